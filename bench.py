@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[1] -- R-MAT scale-22, average degree 16,
+FP32 values, `A.mxv(u, semiring=FP32.PLUS_TIMES)` (SpMV), the configuration the metric
+"SpMV GEdge/s" is quoted on.  A "step" is one SpMV over the whole graph.  With N > 1 the
+matrix is 1-D row-block partitioned by nnz across the ranks (one process per GPU) and each
+step ends with ONE all-gather of the output slices over NCCL so that every rank holds the
+full vector for the next step (strong scaling: the graph is fixed as N grows).
+
+The line also carries the second half of BASELINE.json's metric, SpGEMM Mnnz-out/s, measured
+at N = 1 on configs[3] (R-MAT scale-20 triangle-counting kernel C<L> = L (+.pair) L) under
+"spgemm".
+
+--impl reference times the CPU side: SuiteSparse:GraphBLAS is not installable offline, so the
+reference arm is the OpenMP port in oracle/grb_fast.c (kind "port") on all host cores, on
+the same graph, metric and unit.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "SpMV GEdge/s (R-MAT s22 d16 PLUS_TIMES_FP32 mxv)"
+UNIT = "GEdge/s"
+
+
+# ------------------------------------------------------------------ inputs
+def cached_graph(scale, edgefactor=16, seed=1):
+    """R-MAT CSR (n, indptr, indices), cached under /tmp so both arms / all ranks share one build."""
+    from pygraphblas_b200.generators import rmat_csr
+    base = f"/tmp/b200grb_rmat_s{scale}_e{edgefactor}_seed{seed}"
+    if os.path.exists(base + ".done"):
+        return 1 << scale, np.load(base + "_indptr.npy"), np.load(base + "_indices.npy")
+    n, indptr, indices = rmat_csr(scale, edgefactor, seed)
+    try:
+        np.save(base + "_indptr.npy", indptr)
+        np.save(base + "_indices.npy", indices)
+        open(base + ".done", "w").close()
+    except OSError:
+        pass
+    return n, indptr, indices
+
+
+def spmv_inputs(scale, nnz, n):
+    rng = np.random.default_rng(2)
+    vals = (rng.random(nnz, dtype=np.float32) + np.float32(0.5)).astype(np.float32)    # U[0.5, 1.5)
+    u = rng.random(n, dtype=np.float32)                                                # U[0, 1)
+    return vals, u
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag, self.thread, self.ok = [], set(), False, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max = None
+
+    def _run(self):
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((clk, util))
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.ok:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max, "reasons": [], "samples": 0}
+        loaded = [c for c, u in self.samples if u > 0] or [c for c, _ in self.samples]
+        return {"sm_mhz": float(np.median(loaded)), "sm_max_mhz": self.max, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------ CPU port (reference arm / cpu_baseline)
+def cpu_spmv(n, indptr, indices, vals, u, min_seconds, max_reps):
+    from oracle import oracle as orc
+    L = orc.lib()
+    L.fast_num_threads.restype = ctypes.c_int
+    cores = L.fast_num_threads()
+    w = np.zeros(n, np.float32)
+    pres = np.zeros(n, np.uint8)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    args = (ctypes.c_int64(n), p(indptr), p(indices), p(vals), p(u), p(w), p(pres))
+    L.fast_spmv_plus_times_f32(*args)      # warm-up / page-in
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < max_reps and (time.perf_counter() - t_all < min_seconds or len(times) < 3):
+        t0 = time.perf_counter()
+        L.fast_spmv_plus_times_f32(*args)
+        times.append(time.perf_counter() - t0)
+    return cores, times, w, pres
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, indptr, indices = cached_graph(args.scale)
+    nnz = len(indices)
+    vals, u = spmv_inputs(args.scale, nnz, n)
+    cores, _, _, _ = cpu_spmv(n, indptr, indices, vals, u, 0.0, max(args.warmup, 1))
+    cores, times, _, _ = cpu_spmv(n, indptr, indices, vals, u, 0.0, args.steps)
+    times = times[:args.steps]
+    ms = 1e3 * float(np.mean(times))
+    value = nnz / (ms * 1e-3) / 1e9
+    sample = f"{len(times)} full SpMV passes over the scale-{args.scale} graph ({nnz} edges each)"
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"R-MAT scale-{args.scale} avg-deg-16 FP32 SpMV PLUS_TIMES (BASELINE.json configs[1])",
+                      "n": n, "nnz": nnz, "generator": "Graph500 R-MAT a,b,c,d=.57,.19,.19,.05 ef16 seed 1, dedup",
+                      "note": "CPU OpenMP port of the reference path (SuiteSparse:GraphBLAS not installable offline)"},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------ B200 arm
+class DevArray:
+    """__cuda_array_interface__ view of a raw device pointer (for torch.as_tensor)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference for the CPU port)")
+    os.environ.setdefault("B200GRB_DEVICE", str(local))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import pygraphblas_b200 as gb
+    from pygraphblas_b200 import Matrix, Vector, FP32, INT64, descriptor
+    lib, ffi = gb.lib, gb.ffi
+    sp_ = ffi.new("void**")
+    lib.B200_get_stream(sp_)
+    stream = torch.cuda.ExternalStream(int(ffi.cast("uintptr_t", sp_[0])), device=torch.device("cuda", local))
+
+    # ---- graph (rank 0 builds the cache first, the others read it)
+    if world > 1 and rank != 0:
+        dist.barrier()
+    n, indptr, indices = cached_graph(args.scale)
+    if world > 1 and rank == 0:
+        dist.barrier()
+    nnz = len(indices)
+    vals, u_host0 = spmv_inputs(args.scale, nnz, n)
+    from pygraphblas_b200.generators import row_block_bounds
+    bounds = row_block_bounds(indptr, world)
+    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    k0, k1 = int(indptr[r0]), int(indptr[r1])
+    lptr = (indptr[r0:r1 + 1] - k0).astype(np.int64)
+    A = Matrix.from_csr(lptr, indices[k0:k1], vals[k0:k1], r1 - r0, n, FP32)
+    lnnz, lrows = k1 - k0, r1 - r0
+    u = Vector.from_numpy(u_host0)
+    w = Vector.sparse(FP32, lrows)
+    sr = FP32.PLUS_TIMES
+
+    if world > 1:
+        uptr, _ = u.device_ptrs()
+        u_t = torch.as_tensor(DevArray(uptr, n, "<f4"), device=torch.device("cuda", local))
+        slices = [u_t[int(bounds[r]):int(bounds[r + 1])] for r in range(world)]
+
+    def step():
+        A.mxv(u, semiring=sr, out=w)
+        if world > 1:
+            wptr, _ = w.device_ptrs()
+            w_t = torch.as_tensor(DevArray(wptr, lrows, "<f4"), device=torch.device("cuda", local))
+            with torch.cuda.stream(stream):
+                dist.all_gather(slices, w_t)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        lib.B200_device_synchronize()
+
+    sampler = ClockSampler(local)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    sampler.start()
+    launches0 = lib.B200_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    sync_all()
+    launches = lib.B200_kernel_launches() - launches0
+    ms_total = e0.elapsed_time(e1)
+    # keep the device busy a little longer so that the clock sampler sees the kernel under load
+    t_end = time.perf_counter() + 1.0
+    while time.perf_counter() < t_end:
+        for _ in range(20):
+            A.mxv(u, semiring=sr, out=w)
+        lib.B200_device_synchronize()
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms = ms_total / args.steps
+    value = nnz / (ms * 1e-3) / 1e9
+
+    # ---- kernel-only timing of the local SpMV (no collective) for the roofline
+    sync_all()
+    k0e, k1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0e.record(stream)
+    for _ in range(args.steps):
+        A.mxv(u, semiring=sr, out=w)
+    k1e.record(stream)
+    sync_all()
+    kms = k0e.elapsed_time(k1e) / args.steps
+    alg_bytes = lnnz * 8 + (lrows + 1) * 4 + n * 4 + lrows * 5
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (kms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    if os.path.exists(tpath) and world == 1:
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "spmv_tile_kernel<float,float,PLUS,TIMES> (+ fix-up)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg_bytes,
+                "kernel_ms": kms, "peak_source": peak_src}
+
+    # ---- end to end through the public API with host buffers: H2D u, mxv, D2H w (+ presence)
+    u_pin = torch.empty(n, dtype=torch.float32).pin_memory().numpy()
+    u_pin[:] = u_host0
+    w_pin = torch.empty(lrows, dtype=torch.float32).pin_memory().numpy()
+    p_pin = torch.empty(lrows, dtype=torch.uint8).pin_memory().numpy()
+    ue = Vector.from_numpy(u_pin)
+    we = Vector.sparse(FP32, lrows)
+
+    def e2e_step():
+        ue.set_numpy(u_pin)
+        A.mxv(ue, semiring=sr, out=we)
+        we.to_numpy(out=w_pin, present_out=p_pin)
+
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    sync_all()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": nnz / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(n * 4 * world), "d2h_bytes_per_step": int(n * 5),
+           "ms_per_step": e2e_s * 1e3,
+           "what": "per step: u (pinned host) -> HBM, GrB_mxv through the C ABI, w values + presence -> pinned host; A resident in HBM"}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"R-MAT scale-{args.scale} avg-deg-16 FP32 SpMV PLUS_TIMES (BASELINE.json configs[1])",
+                      "n": n, "nnz": nnz, "generator": "Graph500 R-MAT a,b,c,d=.57,.19,.19,.05 ef16 seed 1, dedup",
+                      "parallelism": f"1-D nnz-balanced row blocks x{world}" + (", one NCCL all-gather of w per step" if world > 1 else ""),
+                      "l2": "inputs (A: %.0f MB) exceed the 126 MB L2; no explicit flush" % (lnnz * 8 / 1e6)},
+           "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+
+    if rank == 0 and world == 1:
+        # ---- CPU baseline on the same workload (bounded sample)
+        cores, times, w_cpu, p_cpu = cpu_spmv(n, indptr, indices, vals, u_host0, args.cpu_seconds, 200)
+        cpu_ms = 1e3 * float(np.mean(times))
+        out["cpu_baseline"] = {"value": nnz / (cpu_ms * 1e-3) / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"{len(times)} full SpMV passes over the same scale-{args.scale} graph, oracle/grb_fast.c OpenMP port"}
+        # parity of the benchmarked result against the CPU port (size-independent check at full size)
+        A.mxv(u, semiring=sr, out=w)
+        xg, pg = w.to_numpy()
+        ok = bool(np.array_equal(pg, p_cpu)) and bool(np.allclose(xg[pg != 0], w_cpu[p_cpu != 0], rtol=2e-5, atol=0))
+        out["parity_full_size"] = ok
+        if not args.no_spgemm:
+            out["spgemm"] = bench_spgemm(args, torch, stream, gb)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_spgemm(args, torch, stream, gb):
+    """BASELINE.json configs[3]: scale-20 triangle-counting kernel C<L> = L (+.pair) L, 1 GPU."""
+    import scipy.sparse as sp
+    from pygraphblas_b200 import Matrix, INT64, descriptor
+    lib = gb.lib
+    scale = args.spgemm_scale
+    n, indptr, indices = cached_graph(scale)
+    S = sp.csr_matrix((np.ones(len(indices), np.int8), indices, indptr), shape=(n, n))
+    Ls = sp.tril(S + S.T, -1).tocsr()
+    Ls.sort_indices()
+    lp, lj = Ls.indptr.astype(np.int64), Ls.indices.astype(np.uint32)
+    nnzL = len(lj)
+    L = Matrix.from_csr(lp, lj, np.ones(nnzL, np.int64), n, n, INT64)
+    C = None
+    for _ in range(2):
+        C = L.mxm(L, mask=L, semiring=INT64.PLUS_PAIR, desc=descriptor.S)
+    lib.B200_device_synchronize()
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.B200_kernel_launches()
+    e0.record(stream)
+    for _ in range(reps):
+        C = L.mxm(L, mask=L, semiring=INT64.PLUS_PAIR, desc=descriptor.S)
+    e1.record(stream)
+    lib.B200_device_synchronize()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = gb.ffi.new("uint64_t*")
+    nout = gb.ffi.new("uint64_t*")
+    lib.B200_last_mxm_stats(flops, nout)
+    tri = int(C.to_arrays()[2].sum())
+    alg = nnzL * 4 + nnzL * 8 + int(flops[0]) * 4 + int(nout[0]) * (4 + 8) + (n + 1) * 8 + nnzL * 4
+    peak, _ = measured_peaks()
+    res = {"workload": f"R-MAT scale-{scale}: L = tril(A+A',-1), C<L> = L (+.pair) L, INT64 (BASELINE.json configs[3])",
+           "value": int(nout[0]) / (ms * 1e-3) / 1e6, "unit": "Mnnz-out/s", "ms": ms, "nnz_L": nnzL, "products": int(flops[0]),
+           "nnz_out": int(nout[0]), "triangles": tri, "gproducts_per_s": int(flops[0]) / (ms * 1e-3) / 1e9,
+           "gpu_launches_per_call": int((lib.B200_kernel_launches() - l0) / reps),
+           "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg, "traffic": None}}
+    # CPU port, one pass
+    from oracle import oracle as orc
+    Lc = orc.lib()
+    cval = np.zeros(nnzL, np.int64)
+    chas = np.zeros(nnzL, np.uint8)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    t0 = time.perf_counter()
+    Lc.fast_masked_saxpy_plus_pair_i64(ctypes.c_int64(n), ctypes.c_int64(n), p(lp), p(lj), p(lp), p(lj), p(lp), p(lj), p(cval), p(chas))
+    cpu_s = time.perf_counter() - t0
+    Lc.fast_num_threads.restype = ctypes.c_int
+    res["cpu_baseline"] = {"value": int(chas.sum()) / cpu_s / 1e6, "unit": "Mnnz-out/s", "cores": Lc.fast_num_threads(), "kind": "port",
+                           "sample": "1 pass of the same masked SpGEMM (oracle/grb_fast.c masked Gustavson, OpenMP)"}
+    res["parity_full_size"] = bool(int(cval.sum()) == tri and int(chas.sum()) == int(nout[0]))
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=int, default=22)
+    ap.add_argument("--spgemm-scale", type=int, default=20)
+    ap.add_argument("--no-spgemm", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,447 @@
+// common.cuh -- internal declarations of libb200grb (not part of the C ABI).
+//
+// Object model behind the opaque GraphBLAS handles of include/b200grb.h, the
+// scalar "carrier" used wherever a value's type is only known at run time
+// (typecasts, accumulators, dup operators), and the typed operator templates
+// that the sm_100a kernels instantiate.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <math.h>
+#include <float.h>
+#include <limits.h>
+#include <string>
+#include <vector>
+#include <mutex>
+#include "../../include/b200grb.h"
+
+#define GB_MAGIC 0x42323030  /* "B200" */
+#define GB_FREED 0x0DEAD000
+
+// ---------------------------------------------------------------- type codes
+enum TypeCode : int {
+    TC_BOOL = 0, TC_INT8, TC_INT16, TC_INT32, TC_INT64,
+    TC_UINT8, TC_UINT16, TC_UINT32, TC_UINT64, TC_FP32, TC_FP64, TC_COUNT
+};
+
+// ---------------------------------------------------------------- operator codes
+enum OpCode : int {
+    OP_FIRST = 0, OP_SECOND, OP_PAIR, OP_ANY, OP_MIN, OP_MAX, OP_PLUS, OP_MINUS, OP_RMINUS,
+    OP_TIMES, OP_DIV, OP_RDIV, OP_POW, OP_ISEQ, OP_ISNE, OP_ISGT, OP_ISLT, OP_ISGE, OP_ISLE,
+    OP_LOR, OP_LAND, OP_LXOR, OP_BOR, OP_BAND, OP_BXOR, OP_BXNOR,
+    OP_EQ, OP_NE, OP_GT, OP_LT, OP_GE, OP_LE,   // z = BOOL
+    OP_USER, OP_COUNT
+};
+static inline bool op_is_cmp(int op) { return op >= OP_EQ && op <= OP_LE; }
+
+// ---------------------------------------------------------------- opaque objects
+struct GB_Type_opaque { int magic; int code; size_t size; const char *name; };
+struct GB_BinaryOp_opaque {
+    int magic; int opcode; GrB_Type xtype, ytype, ztype; const char *name; void *user_fn;
+};
+struct GB_Monoid_opaque { int magic; GrB_BinaryOp op; const char *name; bool builtin; };
+struct GB_Semiring_opaque { int magic; GrB_Monoid add; GrB_BinaryOp mul; const char *name; bool builtin; };
+struct GB_Descriptor_opaque {
+    int magic; int outp, mask, inp0, inp1; int axb; int nthreads; double chunk; int sort;
+    bool builtin; const char *name;
+};
+struct GB_UnaryOp_opaque { int magic; };
+
+// Device CSR panel: rows sorted, columns sorted inside each row.
+struct Csr {
+    int64_t nrows = 0, ncols = 0, nnz = 0;
+    int64_t *rowptr = nullptr;     // [nrows+1] 64-bit offsets (canonical)
+    uint32_t *rowptr32 = nullptr;  // [nrows+1] 32-bit shadow, built when nnz < 2^32
+    uint32_t *col = nullptr;       // [nnz]
+    void *val = nullptr;           // [nnz] of the matrix type
+    // SpMV plan: first row of every TILE-sized slice of the nnz range (spmv.cu)
+    uint32_t *tile_row = nullptr;
+    int64_t ntiles = 0;
+    bool valid = false;
+};
+
+struct GB_Matrix_opaque {
+    int magic; GrB_Type type; uint64_t nrows, ncols;
+    // host form: row-major sorted unique COO
+    std::vector<uint64_t> hi, hj; std::vector<uint8_t> hx; bool host_valid;
+    // pending setElement tuples (in call order; later wins)
+    std::vector<uint64_t> pi, pj; std::vector<uint8_t> px;
+    // device form (+ cached transpose)
+    Csr dev, devT;
+    std::string err;
+};
+
+struct GB_Vector_opaque {
+    int magic; GrB_Type type; uint64_t n;
+    // host form: sorted unique (index, value)
+    std::vector<uint64_t> hi; std::vector<uint8_t> hx; bool host_valid;
+    std::vector<uint64_t> pi; std::vector<uint8_t> px;
+    // device form: dense values + presence bytes (present == nullptr: all present)
+    void *dval = nullptr; uint8_t *dpres = nullptr; bool dev_valid = false; int64_t dev_nvals = -1;
+    std::string err;
+};
+
+// ---------------------------------------------------------------- globals (objects.cu)
+struct GBGlobal {
+    bool initialized = false;
+    bool have_device = false;
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    uint64_t last_flops = 0, last_nnz_out = 0;
+    std::recursive_mutex mu;
+};
+extern GBGlobal G;
+extern thread_local std::string tl_error;
+
+GrB_Info gb_fail(GrB_Info code, std::string *where, const char *fmt, ...);
+
+#define GB_LOCK std::lock_guard<std::recursive_mutex> _lk(G.mu)
+#define GB_CHECK_INIT  do { if (!G.initialized) return gb_fail(GrB_PANIC, nullptr, "GrB_init not called"); } while (0)
+#define GB_TRY(expr) do { GrB_Info _i = (expr); if (_i != GrB_SUCCESS) return _i; } while (0)
+#define CU_TRY(expr, errstr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) \
+    return gb_fail(_e == cudaErrorMemoryAllocation ? GrB_OUT_OF_MEMORY : GrB_PANIC, errstr, \
+                   "CUDA error %s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
+
+// device memory (stream-ordered pool on G.stream)
+GrB_Info dmalloc(void **p, size_t bytes, std::string *err);
+void dfree(void *p);
+template <typename T> static inline GrB_Info dalloc(T **p, size_t count, std::string *err) {
+    return dmalloc((void **)p, count * sizeof(T) + 16, err);   // +16: bulk copies may over-read a tail
+}
+void csr_free(Csr &c);
+
+// host <-> device sync of containers (objects.cu)
+GrB_Info matrix_flush_pending(GrB_Matrix A);
+GrB_Info matrix_ensure_host(GrB_Matrix A);
+GrB_Info matrix_ensure_device(GrB_Matrix A);
+GrB_Info matrix_ensure_transpose(GrB_Matrix A);     // builds A->devT on the device
+void matrix_invalidate_device(GrB_Matrix A);
+void matrix_adopt_device(GrB_Matrix A, Csr &c);     // A takes ownership of c, host form dropped
+GrB_Info vector_ensure_host(GrB_Vector v);
+GrB_Info vector_ensure_device(GrB_Vector v);
+void vector_invalidate_device(GrB_Vector v);
+void vector_adopt_device(GrB_Vector v, void *vals, uint8_t *pres);
+bool gb_valid_matrix(const GrB_Matrix A);
+bool gb_valid_vector(const GrB_Vector v);
+
+struct DescFlags { bool replace, mask_comp, mask_struct, tran0, tran1; int axb; };
+DescFlags desc_flags(const GrB_Descriptor d);
+
+// kernels (device_ops.cu / spmv.cu / spgemm.cu)
+GrB_Info dev_build_rowptr32(Csr &c, std::string *err);
+GrB_Info dev_exclusive_scan(int64_t *data, int64_t n, std::string *err);
+GrB_Info dev_transpose(const Csr &a, size_t vsize, Csr &t, std::string *err);
+GrB_Info dev_cast_values(void **out, int to_code, const void *in, int from_code, int64_t n, std::string *err);
+GrB_Info dev_count_present(const uint8_t *pres, int64_t n, int64_t *count, std::string *err);
+
+// ---------------------------------------------------------------- scalar carrier
+// A value of any builtin type held in 64 bits: BOOL/UINT* in .u, INT* in .i, FP* in .d
+// (a float is held as the exactly-equal double).
+struct Sc { union { int64_t i; uint64_t u; double d; }; };
+
+__host__ __device__ static inline int tc_size(int tc) {
+    switch (tc) {
+        case TC_BOOL: case TC_INT8: case TC_UINT8: return 1;
+        case TC_INT16: case TC_UINT16: return 2;
+        case TC_INT32: case TC_UINT32: case TC_FP32: return 4;
+        default: return 8;
+    }
+}
+__host__ __device__ static inline bool tc_is_float(int tc) { return tc == TC_FP32 || tc == TC_FP64; }
+__host__ __device__ static inline bool tc_is_signed(int tc) { return tc >= TC_INT8 && tc <= TC_INT64; }
+
+__host__ __device__ static inline Sc sc_load(int tc, const void *p, size_t k) {
+    Sc s; s.u = 0;
+    switch (tc) {
+        case TC_BOOL:   s.u = ((const uint8_t *)p)[k] != 0; break;
+        case TC_INT8:   s.i = ((const int8_t *)p)[k]; break;
+        case TC_INT16:  s.i = ((const int16_t *)p)[k]; break;
+        case TC_INT32:  s.i = ((const int32_t *)p)[k]; break;
+        case TC_INT64:  s.i = ((const int64_t *)p)[k]; break;
+        case TC_UINT8:  s.u = ((const uint8_t *)p)[k]; break;
+        case TC_UINT16: s.u = ((const uint16_t *)p)[k]; break;
+        case TC_UINT32: s.u = ((const uint32_t *)p)[k]; break;
+        case TC_UINT64: s.u = ((const uint64_t *)p)[k]; break;
+        case TC_FP32:   s.d = (double)((const float *)p)[k]; break;
+        case TC_FP64:   s.d = ((const double *)p)[k]; break;
+    }
+    return s;
+}
+__host__ __device__ static inline void sc_store(int tc, void *p, size_t k, Sc s) {
+    switch (tc) {
+        case TC_BOOL:   ((uint8_t *)p)[k] = (uint8_t)(s.u != 0); break;
+        case TC_INT8:   ((int8_t *)p)[k] = (int8_t)s.i; break;
+        case TC_INT16:  ((int16_t *)p)[k] = (int16_t)s.i; break;
+        case TC_INT32:  ((int32_t *)p)[k] = (int32_t)s.i; break;
+        case TC_INT64:  ((int64_t *)p)[k] = s.i; break;
+        case TC_UINT8:  ((uint8_t *)p)[k] = (uint8_t)s.u; break;
+        case TC_UINT16: ((uint16_t *)p)[k] = (uint16_t)s.u; break;
+        case TC_UINT32: ((uint32_t *)p)[k] = (uint32_t)s.u; break;
+        case TC_UINT64: ((uint64_t *)p)[k] = s.u; break;
+        case TC_FP32:   ((float *)p)[k] = (float)s.d; break;
+        case TC_FP64:   ((double *)p)[k] = s.d; break;
+    }
+}
+
+// float -> integer conversion as GraphBLAS defines it (NaN -> 0, saturate, truncate).
+__host__ __device__ static inline int64_t sat_i64(double d, int64_t lo, int64_t hi) {
+    if (d != d) return 0;
+    if (d <= (double)lo) return lo;
+    if (d >= (double)hi) return hi;
+    return (int64_t)d;
+}
+__host__ __device__ static inline uint64_t sat_u64(double d, uint64_t hi) {
+    if (d != d) return 0;
+    if (d <= 0.0) return 0;
+    if (d >= (double)hi) return hi;
+    return (uint64_t)d;
+}
+
+// C-style typecast between builtin types, on the carrier.
+__host__ __device__ static inline Sc sc_cast(Sc x, int from, int to) {
+    if (from == to) return x;
+    Sc r; r.u = 0;
+    const bool ff = tc_is_float(from), fs = tc_is_signed(from);
+    if (to == TC_BOOL) { r.u = ff ? (x.d != 0.0) : (x.u != 0); return r; }
+    if (to == TC_FP64) { r.d = ff ? x.d : (fs ? (double)x.i : (double)x.u); return r; }
+    if (to == TC_FP32) { r.d = ff ? (double)(float)x.d : (fs ? (double)(float)x.i : (double)(float)x.u); return r; }
+    if (ff) {
+        switch (to) {
+            case TC_INT8:   r.i = sat_i64(x.d, INT8_MIN, INT8_MAX); break;
+            case TC_INT16:  r.i = sat_i64(x.d, INT16_MIN, INT16_MAX); break;
+            case TC_INT32:  r.i = sat_i64(x.d, INT32_MIN, INT32_MAX); break;
+            case TC_INT64:  r.i = sat_i64(x.d, INT64_MIN, INT64_MAX); break;
+            case TC_UINT8:  r.u = sat_u64(x.d, UINT8_MAX); break;
+            case TC_UINT16: r.u = sat_u64(x.d, UINT16_MAX); break;
+            case TC_UINT32: r.u = sat_u64(x.d, UINT32_MAX); break;
+            case TC_UINT64: r.u = sat_u64(x.d, UINT64_MAX); break;
+        }
+        return r;
+    }
+    // integer/bool -> integer: modular truncation, then sign- or zero-extension
+    switch (to) {
+        case TC_INT8:   r.i = (int8_t)x.u; break;
+        case TC_INT16:  r.i = (int16_t)x.u; break;
+        case TC_INT32:  r.i = (int32_t)x.u; break;
+        case TC_INT64:  r.i = (int64_t)x.u; break;
+        case TC_UINT8:  r.u = (uint8_t)x.u; break;
+        case TC_UINT16: r.u = (uint16_t)x.u; break;
+        case TC_UINT32: r.u = (uint32_t)x.u; break;
+        case TC_UINT64: r.u = x.u; break;
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------- typed operators
+template <typename T> struct TypeOf;
+template <> struct TypeOf<bool>     { static constexpr int code = TC_BOOL; };
+template <> struct TypeOf<int8_t>   { static constexpr int code = TC_INT8; };
+template <> struct TypeOf<int16_t>  { static constexpr int code = TC_INT16; };
+template <> struct TypeOf<int32_t>  { static constexpr int code = TC_INT32; };
+template <> struct TypeOf<int64_t>  { static constexpr int code = TC_INT64; };
+template <> struct TypeOf<uint8_t>  { static constexpr int code = TC_UINT8; };
+template <> struct TypeOf<uint16_t> { static constexpr int code = TC_UINT16; };
+template <> struct TypeOf<uint32_t> { static constexpr int code = TC_UINT32; };
+template <> struct TypeOf<uint64_t> { static constexpr int code = TC_UINT64; };
+template <> struct TypeOf<float>    { static constexpr int code = TC_FP32; };
+template <> struct TypeOf<double>   { static constexpr int code = TC_FP64; };
+
+template <typename T> struct NumTraits {
+    static constexpr bool is_float = false;
+    static constexpr bool is_signed = ((T)-1) < (T)0;
+    __host__ __device__ static inline T maxv() {
+        return is_signed ? (T)((((uint64_t)1) << (sizeof(T) * 8 - 1)) - 1) : (T)~(T)0;
+    }
+    __host__ __device__ static inline T minv() {
+        return is_signed ? (T)(((uint64_t)1) << (sizeof(T) * 8 - 1)) : (T)0;
+    }
+};
+template <> struct NumTraits<float> {
+    static constexpr bool is_float = true; static constexpr bool is_signed = true;
+    __host__ __device__ static inline float maxv() { return INFINITY; }
+    __host__ __device__ static inline float minv() { return -INFINITY; }
+};
+template <> struct NumTraits<double> {
+    static constexpr bool is_float = true; static constexpr bool is_signed = true;
+    __host__ __device__ static inline double maxv() { return (double)INFINITY; }
+    __host__ __device__ static inline double minv() { return -(double)INFINITY; }
+};
+
+template <typename T> struct UnsignedOf { typedef T type; };
+template <> struct UnsignedOf<int8_t>  { typedef uint8_t type; };
+template <> struct UnsignedOf<int16_t> { typedef uint16_t type; };
+template <> struct UnsignedOf<int32_t> { typedef uint32_t type; };
+template <> struct UnsignedOf<int64_t> { typedef uint64_t type; };
+
+template <typename T> __host__ __device__ static inline T t_from_double(double d) {
+    if (NumTraits<T>::is_float) return (T)d;
+    if (NumTraits<T>::is_signed) return (T)sat_i64(d, (int64_t)NumTraits<T>::minv(), (int64_t)NumTraits<T>::maxv());
+    return (T)sat_u64(d, (uint64_t)NumTraits<T>::maxv());
+}
+
+// integer division with GraphBLAS' defined results for x/0 and INT_MIN/-1
+template <typename T> __host__ __device__ static inline T int_div(T x, T y) {
+    if constexpr (NumTraits<T>::is_signed) {
+        if (y == (T)-1) return (T)(0 - (typename UnsignedOf<T>::type)x);
+        if (y == 0) return x == 0 ? (T)0 : (x < 0 ? NumTraits<T>::minv() : NumTraits<T>::maxv());
+        return (T)(x / y);
+    } else {
+        if (y == 0) return x == 0 ? (T)0 : NumTraits<T>::maxv();
+        return (T)(x / y);
+    }
+}
+
+// z = op(x, y) with z of the operand type T (arithmetic, logical and IS* operators).
+template <typename T> __host__ __device__ __forceinline__ T op_apply(int op, T x, T y) {
+    typedef typename UnsignedOf<T>::type U;
+    constexpr bool F = NumTraits<T>::is_float;
+    switch (op) {
+        case OP_FIRST:  return x;
+        case OP_SECOND: return y;
+        case OP_ANY:    return x;
+        case OP_PAIR:   return (T)1;
+        case OP_MIN:    if (F) return (T)fmin((double)x, (double)y); return x < y ? x : y;
+        case OP_MAX:    if (F) return (T)fmax((double)x, (double)y); return x > y ? x : y;
+        case OP_PLUS:   if (F) return x + y; return (T)((U)x + (U)y);
+        case OP_MINUS:  if (F) return x - y; return (T)((U)x - (U)y);
+        case OP_RMINUS: if (F) return y - x; return (T)((U)y - (U)x);
+        case OP_TIMES:  if (F) return x * y; return (T)((U)x * (U)y);
+        case OP_DIV:    if constexpr (F) return x / y; else return int_div<T>(x, y);
+        case OP_RDIV:   if constexpr (F) return y / x; else return int_div<T>(y, x);
+        case OP_POW:    return t_from_double<T>(pow((double)x, (double)y));
+        case OP_ISEQ:   return (T)(x == y);
+        case OP_ISNE:   return (T)(x != y);
+        case OP_ISGT:   return (T)(x > y);
+        case OP_ISLT:   return (T)(x < y);
+        case OP_ISGE:   return (T)(x >= y);
+        case OP_ISLE:   return (T)(x <= y);
+        case OP_LOR:    return (T)((x != 0) || (y != 0));
+        case OP_LAND:   return (T)((x != 0) && (y != 0));
+        case OP_LXOR:   return (T)((x != 0) != (y != 0));
+        case OP_BOR:    if constexpr (F) return x; else return (T)((U)x | (U)y);
+        case OP_BAND:   if constexpr (F) return x; else return (T)((U)x & (U)y);
+        case OP_BXOR:   if constexpr (F) return x; else return (T)((U)x ^ (U)y);
+        case OP_BXNOR:  if constexpr (F) return x; else return (T)~((U)x ^ (U)y);
+        default:        return x;
+    }
+}
+template <> __host__ __device__ __forceinline__ float op_apply<float>(int op, float x, float y) {
+    switch (op) {
+        case OP_FIRST: case OP_ANY: return x;
+        case OP_SECOND: return y;
+        case OP_PAIR:   return 1.0f;
+        case OP_MIN:    return fminf(x, y);
+        case OP_MAX:    return fmaxf(x, y);
+        case OP_PLUS:   return x + y;
+        case OP_MINUS:  return x - y;
+        case OP_RMINUS: return y - x;
+        case OP_TIMES:  return x * y;
+        case OP_DIV:    return x / y;
+        case OP_RDIV:   return y / x;
+        case OP_POW:    return powf(x, y);
+        case OP_ISEQ:   return (float)(x == y);
+        case OP_ISNE:   return (float)(x != y);
+        case OP_ISGT:   return (float)(x > y);
+        case OP_ISLT:   return (float)(x < y);
+        case OP_ISGE:   return (float)(x >= y);
+        case OP_ISLE:   return (float)(x <= y);
+        case OP_LOR:    return (float)((x != 0) || (y != 0));
+        case OP_LAND:   return (float)((x != 0) && (y != 0));
+        case OP_LXOR:   return (float)((x != 0) != (y != 0));
+        default:        return x;
+    }
+}
+// BOOL: arithmetic names alias logical ones (PLUS=LOR, TIMES=LAND, MIN=LAND, MAX=LOR, MINUS=LXOR, DIV=FIRST ...)
+template <> __host__ __device__ __forceinline__ bool op_apply<bool>(int op, bool x, bool y) {
+    switch (op) {
+        case OP_FIRST: case OP_ANY: case OP_DIV: return x;
+        case OP_SECOND: case OP_RDIV: return y;
+        case OP_PAIR:   return true;
+        case OP_MIN: case OP_TIMES: case OP_LAND: return x && y;
+        case OP_MAX: case OP_PLUS: case OP_LOR: return x || y;
+        case OP_MINUS: case OP_RMINUS: case OP_LXOR: case OP_ISNE: return x != y;
+        case OP_POW:    return x || !y;
+        case OP_ISEQ:   return x == y;
+        case OP_ISGT:   return x && !y;
+        case OP_ISLT:   return !x && y;
+        case OP_ISGE:   return x || !y;
+        case OP_ISLE:   return !x || y;
+        default:        return x;
+    }
+}
+// z = cmp(x, y), z BOOL
+template <typename T> __host__ __device__ __forceinline__ bool cmp_apply(int op, T x, T y) {
+    switch (op) {
+        case OP_EQ: return x == y;
+        case OP_NE: return x != y;
+        case OP_GT: return x > y;
+        case OP_LT: return x < y;
+        case OP_GE: return x >= y;
+        case OP_LE: return x <= y;
+        default:    return false;
+    }
+}
+// multiply of a semiring: ZT == XT for arithmetic operators, ZT == bool for comparisons
+template <typename XT, typename ZT> struct MulApply {
+    __host__ __device__ static __forceinline__ ZT f(int op, XT a, XT b) { return (ZT)cmp_apply<XT>(op, a, b); }
+};
+template <typename T> struct MulApply<T, T> {
+    __host__ __device__ static __forceinline__ T f(int op, T a, T b) {
+        if (op >= OP_EQ && op <= OP_LE) return (T)cmp_apply<T>(op, a, b);
+        return op_apply<T>(op, a, b);
+    }
+};
+
+// identity / terminal value of a monoid operator on type T
+template <typename T> __host__ __device__ static inline T monoid_identity(int op) {
+    switch (op) {
+        case OP_MIN:   return NumTraits<T>::maxv();
+        case OP_MAX:   return NumTraits<T>::minv();
+        case OP_TIMES: return (T)1;
+        case OP_LAND:  return (T)1;
+        case OP_EQ:    return (T)1;
+        case OP_BAND: case OP_BXNOR: return (T)~(uint64_t)0;
+        default:       return (T)0;   // PLUS, LOR, LXOR, ANY, BOR, BXOR
+    }
+}
+template <> __host__ __device__ inline bool monoid_identity<bool>(int op) {
+    switch (op) {
+        case OP_MIN: case OP_TIMES: case OP_LAND: case OP_EQ: return true;
+        default: return false;
+    }
+}
+template <> __host__ __device__ inline float monoid_identity<float>(int op) {
+    switch (op) { case OP_MIN: return INFINITY; case OP_MAX: return -INFINITY;
+                  case OP_TIMES: case OP_LAND: case OP_EQ: return 1.0f; default: return 0.0f; }
+}
+template <> __host__ __device__ inline double monoid_identity<double>(int op) {
+    switch (op) { case OP_MIN: return (double)INFINITY; case OP_MAX: return -(double)INFINITY;
+                  case OP_TIMES: case OP_LAND: case OP_EQ: return 1.0; default: return 0.0; }
+}
+
+// carrier-level operator: x, y, z all of the operator's type `tc` (z BOOL for comparisons)
+__host__ __device__ static inline Sc sc_binop(int op, int tc, Sc x, Sc y) {
+    Sc r; r.u = 0;
+#define GB_CASE(TC, T, FIELD) case TC: { T a = (T)x.FIELD, b = (T)y.FIELD; \
+        if (op >= OP_EQ && op <= OP_LE) r.u = cmp_apply<T>(op, a, b); \
+        else { T z = op_apply<T>(op, a, b); Sc t; t.u = 0; t.FIELD = z; r = t; } } break;
+    switch (tc) {
+        case TC_BOOL: { bool a = x.u != 0, b = y.u != 0;
+            if (op >= OP_EQ && op <= OP_LE) r.u = cmp_apply<bool>(op, a, b); else r.u = op_apply<bool>(op, a, b); } break;
+        GB_CASE(TC_INT8, int8_t, i) GB_CASE(TC_INT16, int16_t, i) GB_CASE(TC_INT32, int32_t, i) GB_CASE(TC_INT64, int64_t, i)
+        GB_CASE(TC_UINT8, uint8_t, u) GB_CASE(TC_UINT16, uint16_t, u) GB_CASE(TC_UINT32, uint32_t, u) GB_CASE(TC_UINT64, uint64_t, u)
+        case TC_FP32: { float a = (float)x.d, b = (float)y.d;
+            if (op >= OP_EQ && op <= OP_LE) r.u = cmp_apply<float>(op, a, b); else r.d = (double)op_apply<float>(op, a, b); } break;
+        case TC_FP64: { double a = x.d, b = y.d;
+            if (op >= OP_EQ && op <= OP_LE) r.u = cmp_apply<double>(op, a, b); else r.d = op_apply<double>(op, a, b); } break;
+    }
+#undef GB_CASE
+    return r;
+}
+
+// ---------------------------------------------------------------- launch helpers
+__host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+#define GB_LAUNCHED() (G.launches++)

@@ -1,0 +1,450 @@
+// spmv.cu -- GrB_mxv / GrB_vxm on sm_100a:  w<mask> = accum(w, op(A) (+).(x) u)
+//
+// Replaces the SuiteSparse call behind /root/reference/pygraphblas/matrix.py:2716
+// (Matrix.mxv) and /root/reference/pygraphblas/vector.py:961 (Vector.vxm).
+//
+// Layout in HBM: A is CSR (32-bit row offsets shadow, 32-bit column ids, values of
+// the matrix type), vectors are dense value arrays + one presence byte per position
+// (no presence array at all when every position is present).
+//
+// Kernel (spmv_tile_kernel): nnz-split, row-segmented.  The nnz range is cut into
+// fixed tiles of SPMV_TILE entries, one CTA per tile, so R-MAT hub rows cannot
+// serialise a warp.  Each thread streams its slice of colidx/values with 128-bit
+// coalesced loads, gathers u[col] (L2-resident), and parks the products in shared
+// memory; the CTA then reduces the row segments that fall inside the tile
+// (thread-per-row for short segments, warp-per-row for long ones).  Rows that
+// straddle tile boundaries leave per-tile head/tail partials that a small fix-up
+// kernel combines in a fixed order -- the result is deterministic for a given matrix.
+//
+// Algorithmic bytes per call: nnz*(4 + sizeof(a)) + (nrows+1)*4
+//   + ncols*sizeof(u) + nrows*(sizeof(t) + 1).
+#include "common.cuh"
+#include <algorithm>
+
+GrB_Info dev_exclusive_scan(int64_t *data, int64_t n, std::string *err);
+
+static constexpr int SPMV_THREADS = 256;
+static constexpr int SPMV_VEC = 4;                       // entries per 128-bit column load
+static constexpr int SPMV_GROUPS = 2;                    // 128-bit loads per thread per array
+static constexpr int SPMV_TILE = SPMV_THREADS * SPMV_VEC * SPMV_GROUPS;   // 2048 nnz per CTA
+static constexpr int SPMV_LONG = 64;                     // segments longer than this go warp-per-row
+static constexpr int SPMV_QUEUE = SPMV_TILE / SPMV_LONG + 1;
+
+struct SpmvArgs {
+    const uint32_t *rowptr; const uint32_t *col; const void *aval;
+    const uint32_t *tile_row; int64_t ntiles; int64_t nrows; int64_t nnz;
+    const void *uval; const uint8_t *upres;
+    void *tval; uint8_t *tpres;
+    void *head_val; uint8_t *head_has; void *tail_val; uint8_t *tail_has; int32_t *tail_row;
+    int add_op, mul_op;
+    int flip;      // 0: z = mul(a, u) (mxv)   1: z = mul(u, a) (vxm)
+    int need_a;    // the multiply reads A's value
+    int need_u;    // the multiply reads u's value
+};
+
+// ---- plan: tile_row[t] = row holding nnz t*TILE (tile_row[0] = 0, tile_row[ntiles] = nrows)
+__global__ void spmv_plan_kernel(const uint32_t *rowptr, int64_t nrows, int64_t ntiles, uint32_t *tile_row) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) return;
+    if (t == 0) { tile_row[0] = 0; return; }
+    if (t == ntiles) { tile_row[t] = (uint32_t)nrows; return; }
+    const uint32_t x = (uint32_t)(t * SPMV_TILE);
+    int64_t lo = 0, hi = nrows;           // first r in [0, nrows] with rowptr[r] > x
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (rowptr[mid] > x) hi = mid; else lo = mid + 1; }
+    tile_row[t] = (uint32_t)(lo - 1);
+}
+
+static GrB_Info spmv_plan(Csr &c, std::string *err) {
+    if (c.tile_row) return GrB_SUCCESS;
+    if (!c.rowptr32) return gb_fail(GrB_INVALID_VALUE, err, "mxv: matrices with >= 2^32 entries are not supported");
+    c.ntiles = ceil_div(c.nnz, SPMV_TILE);
+    GB_TRY(dalloc(&c.tile_row, (size_t)c.ntiles + 1, err));
+    const int64_t n = c.ntiles + 1;
+    spmv_plan_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, G.stream>>>(c.rowptr32, c.nrows, c.ntiles, c.tile_row); GB_LAUNCHED();
+    CU_TRY(cudaGetLastError(), err);
+    return GrB_SUCCESS;
+}
+
+// ---- 128-bit-granular loads of four consecutive entries
+template <typename T> __device__ __forceinline__ void load4(const T *p, T (&out)[4]) {
+    if constexpr (sizeof(T) == 4) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+        out[0] = reinterpret_cast<const T &>(v.x); out[1] = reinterpret_cast<const T &>(v.y);
+        out[2] = reinterpret_cast<const T &>(v.z); out[3] = reinterpret_cast<const T &>(v.w);
+    } else if constexpr (sizeof(T) == 8) {
+        const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(p));
+        const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+        uint64_t q[4] = {((uint64_t)v0.y << 32) | v0.x, ((uint64_t)v0.w << 32) | v0.z,
+                         ((uint64_t)v1.y << 32) | v1.x, ((uint64_t)v1.w << 32) | v1.z};
+        for (int k = 0; k < 4; ++k) out[k] = reinterpret_cast<const T &>(q[k]);
+    } else if constexpr (sizeof(T) == 2) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+        uint16_t q[4] = {(uint16_t)(v.x & 0xffff), (uint16_t)(v.x >> 16), (uint16_t)(v.y & 0xffff), (uint16_t)(v.y >> 16)};
+        for (int k = 0; k < 4; ++k) out[k] = reinterpret_cast<const T &>(q[k]);
+    } else {
+        const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(p));
+        uint8_t q[4] = {(uint8_t)(v & 0xff), (uint8_t)((v >> 8) & 0xff), (uint8_t)((v >> 16) & 0xff), (uint8_t)(v >> 24)};
+        for (int k = 0; k < 4; ++k) out[k] = reinterpret_cast<const T &>(q[k]);
+    }
+}
+
+template <typename T> __device__ __forceinline__ T gload(const T *p) {
+    if constexpr (sizeof(T) == 1) { const unsigned char v = __ldg(reinterpret_cast<const unsigned char *>(p)); return reinterpret_cast<const T &>(v); }
+    else return __ldg(p);
+}
+
+template <typename T> __device__ __forceinline__ T shfl_xor_t(T v, int o) {
+    if constexpr (sizeof(T) == 8) {
+        long long x = reinterpret_cast<long long &>(v);
+        x = __shfl_xor_sync(0xffffffffu, x, o);
+        return reinterpret_cast<T &>(x);
+    } else if constexpr (sizeof(T) == 4) {
+        int x = reinterpret_cast<int &>(v);
+        x = __shfl_xor_sync(0xffffffffu, x, o);
+        return reinterpret_cast<T &>(x);
+    } else {
+        int x = (int)v;
+        x = __shfl_xor_sync(0xffffffffu, x, o);
+        return (T)x;
+    }
+}
+
+__device__ __forceinline__ int pad_idx(int i) { return i + (i >> 5); }   // breaks power-of-two strides
+
+template <typename XT, typename ZT, int ADD, int MUL>
+__global__ void __launch_bounds__(SPMV_THREADS) spmv_tile_kernel(const SpmvArgs p) {
+    __shared__ ZT s_prod[SPMV_TILE + SPMV_TILE / 32];
+    __shared__ uint8_t s_has[SPMV_TILE + SPMV_TILE / 32];
+    __shared__ int s_queue[SPMV_QUEUE];
+    __shared__ int s_qcount;
+
+    const int add = ADD >= 0 ? ADD : p.add_op;
+    const int mul = MUL >= 0 ? MUL : p.mul_op;
+    const ZT ident = monoid_identity<ZT>(add);
+    const int64_t tile = blockIdx.x;
+    const int64_t tstart = tile * SPMV_TILE;
+    const int64_t tend = min(tstart + (int64_t)SPMV_TILE, p.nnz);
+    const bool last = tile == p.ntiles - 1;
+    const bool sparse_u = p.upres != nullptr;
+    const XT *aval = static_cast<const XT *>(p.aval);
+    const XT *uval = static_cast<const XT *>(p.uval);
+    ZT *tval = static_cast<ZT *>(p.tval);
+
+    if (threadIdx.x == 0) { s_qcount = 0; p.tail_row[tile] = -1; p.head_has[tile] = 0; p.tail_has[tile] = 0; }
+
+    // ---- stream the tile: 128-bit column / value loads, gather u, products to shared memory
+#pragma unroll
+    for (int g = 0; g < SPMV_GROUPS; ++g) {
+        const int loc = g * SPMV_THREADS * SPMV_VEC + threadIdx.x * SPMV_VEC;
+        const int64_t k0 = tstart + loc;
+        uint32_t c[4]; XT a[4]; bool ok[4];
+        if (k0 + 3 < tend) {
+            load4<uint32_t>(p.col + k0, c);
+            if (p.need_a) load4<XT>(aval + k0, a);
+            ok[0] = ok[1] = ok[2] = ok[3] = true;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                ok[j] = k0 + j < tend;
+                c[j] = ok[j] ? p.col[k0 + j] : 0u;
+                if (p.need_a && ok[j]) a[j] = aval[k0 + j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ZT z = ident; uint8_t has = 0;
+            if (ok[j]) {
+                has = sparse_u ? __ldg(p.upres + c[j]) : (uint8_t)1;
+                if (has) {
+                    const XT av = p.need_a ? a[j] : (XT)1;
+                    const XT uv = p.need_u ? gload<XT>(uval + c[j]) : (XT)1;
+                    z = p.flip ? MulApply<XT, ZT>::f(mul, uv, av) : MulApply<XT, ZT>::f(mul, av, uv);
+                }
+            }
+            s_prod[pad_idx(loc + j)] = z;
+            if (sparse_u) s_has[pad_idx(loc + j)] = has;
+        }
+    }
+    __syncthreads();
+
+    // ---- reduce the row segments inside the tile
+    const int64_t r0 = p.tile_row[tile];
+    const int64_t r1 = min((int64_t)p.tile_row[tile + 1], p.nrows - 1);
+    auto emit = [&](int64_t r, int64_t rs, int64_t re, ZT acc, uint8_t has) {
+        if (rs >= tstart && re <= tend) { tval[r] = acc; p.tpres[r] = has; }
+        else if (rs < tstart) { static_cast<ZT *>(p.head_val)[tile] = acc; p.head_has[tile] = has; }
+        else { static_cast<ZT *>(p.tail_val)[tile] = acc; p.tail_has[tile] = has; p.tail_row[tile] = (int32_t)r; }
+    };
+    for (int64_t r = r0 + threadIdx.x; r <= r1; r += SPMV_THREADS) {
+        const int64_t rs = p.rowptr[r], re = p.rowptr[r + 1];
+        if (rs == re) { p.tpres[r] = 0; tval[r] = (ZT)0; continue; }                    // empty row: no entry
+        if (rs >= tend && !last) continue;                             // starts in the next tile
+        const int s = (int)(max(rs, tstart) - tstart), e = (int)(min(re, tend) - tstart);
+        if (e - s > SPMV_LONG) { s_queue[atomicAdd(&s_qcount, 1)] = (int)(r - r0); continue; }
+        ZT acc = ident; uint8_t has = sparse_u ? 0 : 1;
+        for (int k = s; k < e; ++k) {
+            acc = MulApply<ZT, ZT>::f(add, acc, s_prod[pad_idx(k)]);
+            if (sparse_u) has |= s_has[pad_idx(k)];
+        }
+        emit(r, rs, re, acc, has);
+    }
+    __syncthreads();
+    const int nq = s_qcount;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = warp; q < nq; q += SPMV_THREADS / 32) {
+        const int64_t r = r0 + s_queue[q];
+        const int64_t rs = p.rowptr[r], re = p.rowptr[r + 1];
+        const int s = (int)(max(rs, tstart) - tstart), e = (int)(min(re, tend) - tstart);
+        ZT acc = ident; int has = sparse_u ? 0 : 1;
+        for (int k = s + lane; k < e; k += 32) {
+            acc = MulApply<ZT, ZT>::f(add, acc, s_prod[pad_idx(k)]);
+            if (sparse_u) has |= s_has[pad_idx(k)];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc = MulApply<ZT, ZT>::f(add, acc, shfl_xor_t<ZT>(acc, o));
+            has |= __shfl_xor_sync(0xffffffffu, has, o);
+        }
+        if (lane == 0) emit(r, rs, re, acc, (uint8_t)has);
+    }
+}
+
+// ---- fix-up: rows that straddle tiles = tail partial of the tile they start in
+//      (+) head partials of the following tiles, combined by one warp in a fixed order
+template <typename ZT, int ADD>
+__global__ void __launch_bounds__(256) spmv_fixup_kernel(const SpmvArgs p) {
+    const int add = ADD >= 0 ? ADD : p.add_op;
+    const int lane = threadIdx.x & 31;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= p.ntiles) return;
+    const int32_t r = p.tail_row[t];
+    if (r < 0) return;
+    const ZT ident = monoid_identity<ZT>(add);
+    const int64_t re = p.rowptr[r + 1];
+    const int64_t last_tile = (re - 1) / SPMV_TILE;
+    ZT acc = ident; int has = 0;
+    if (lane == 0) { acc = static_cast<const ZT *>(p.tail_val)[t]; has = p.tail_has[t]; }
+    for (int64_t tt = t + 1 + lane; tt <= last_tile; tt += 32) {
+        acc = MulApply<ZT, ZT>::f(add, acc, static_cast<const ZT *>(p.head_val)[tt]);
+        has |= p.head_has[tt];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc = MulApply<ZT, ZT>::f(add, acc, shfl_xor_t<ZT>(acc, o));
+        has |= __shfl_xor_sync(0xffffffffu, has, o);
+    }
+    if (lane == 0) { static_cast<ZT *>(p.tval)[r] = acc; p.tpres[r] = (uint8_t)(has != 0); }
+}
+
+__global__ void clear_presence_kernel(uint8_t *p, int64_t n) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) p[k] = 0;
+}
+
+template <typename XT, typename ZT, int ADD, int MUL>
+static void spmv_launch(const SpmvArgs &a) {
+    spmv_tile_kernel<XT, ZT, ADD, MUL><<<(unsigned)a.ntiles, SPMV_THREADS, 0, G.stream>>>(a); GB_LAUNCHED();
+    spmv_fixup_kernel<ZT, ADD><<<(unsigned)ceil_div(a.ntiles * 32, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED();
+}
+
+// compile-time specialised semirings (BASELINE.json north_star: PLUS_TIMES, LOR_LAND, MIN_PLUS,
+// PLUS_SECOND; plus PLUS_PAIR / ANY_PAIR / PLUS_FIRST / MIN_FIRST / MIN_SECOND which the reference's
+// demos use); everything else runs the same kernel with run-time operator codes.
+template <typename T> static bool spmv_fast(int add, int mul, const SpmvArgs &a) {
+#define GB_FAST(A, M) if (add == A && mul == M) { spmv_launch<T, T, A, M>(a); return true; }
+    GB_FAST(OP_PLUS, OP_TIMES) GB_FAST(OP_MIN, OP_PLUS) GB_FAST(OP_PLUS, OP_SECOND) GB_FAST(OP_PLUS, OP_FIRST)
+    GB_FAST(OP_PLUS, OP_PAIR) GB_FAST(OP_MIN, OP_FIRST) GB_FAST(OP_MIN, OP_SECOND)
+#undef GB_FAST
+    return false;
+}
+static bool spmv_fast_bool(int add, int mul, const SpmvArgs &a) {
+#define GB_FAST(A, M) if (add == A && mul == M) { spmv_launch<bool, bool, A, M>(a); return true; }
+    GB_FAST(OP_LOR, OP_LAND) GB_FAST(OP_ANY, OP_PAIR) GB_FAST(OP_LOR, OP_PAIR) GB_FAST(OP_LOR, OP_SECOND) GB_FAST(OP_LOR, OP_FIRST)
+#undef GB_FAST
+    return false;
+}
+
+static GrB_Info spmv_dispatch(int xt, int zt, int add, int mul, const SpmvArgs &a, std::string *err) {
+    if (xt == zt) {
+        switch (xt) {
+            case TC_FP32:  if (spmv_fast<float>(add, mul, a)) return GrB_SUCCESS; break;
+            case TC_FP64:  if (spmv_fast<double>(add, mul, a)) return GrB_SUCCESS; break;
+            case TC_INT32: if (spmv_fast<int32_t>(add, mul, a)) return GrB_SUCCESS; break;
+            case TC_INT64: if (spmv_fast<int64_t>(add, mul, a)) return GrB_SUCCESS; break;
+            case TC_UINT32: if (spmv_fast<uint32_t>(add, mul, a)) return GrB_SUCCESS; break;
+            case TC_UINT64: if (spmv_fast<uint64_t>(add, mul, a)) return GrB_SUCCESS; break;
+            case TC_BOOL:  if (spmv_fast_bool(add, mul, a)) return GrB_SUCCESS; break;
+            default: break;
+        }
+        switch (xt) {
+#define GB_GEN(TC, T) case TC: spmv_launch<T, T, -1, -1>(a); return GrB_SUCCESS;
+            GB_GEN(TC_BOOL, bool) GB_GEN(TC_INT8, int8_t) GB_GEN(TC_INT16, int16_t) GB_GEN(TC_INT32, int32_t) GB_GEN(TC_INT64, int64_t)
+            GB_GEN(TC_UINT8, uint8_t) GB_GEN(TC_UINT16, uint16_t) GB_GEN(TC_UINT32, uint32_t) GB_GEN(TC_UINT64, uint64_t)
+            GB_GEN(TC_FP32, float) GB_GEN(TC_FP64, double)
+#undef GB_GEN
+        }
+    } else if (zt == TC_BOOL) {
+        switch (xt) {
+#define GB_GEN(TC, T) case TC: spmv_launch<T, bool, -1, -1>(a); return GrB_SUCCESS;
+            GB_GEN(TC_INT8, int8_t) GB_GEN(TC_INT16, int16_t) GB_GEN(TC_INT32, int32_t) GB_GEN(TC_INT64, int64_t)
+            GB_GEN(TC_UINT8, uint8_t) GB_GEN(TC_UINT16, uint16_t) GB_GEN(TC_UINT32, uint32_t) GB_GEN(TC_UINT64, uint64_t)
+            GB_GEN(TC_FP32, float) GB_GEN(TC_FP64, double)
+#undef GB_GEN
+        }
+    }
+    return gb_fail(GrB_DOMAIN_MISMATCH, err, "mxv: unsupported semiring domains (x=%d, z=%d)", xt, zt);
+}
+
+// ------------------------------------------------------------------ finalize:  w<mask> = accum(w, t)
+struct VecFinalizeArgs {
+    int64_t n;
+    const void *wval; const uint8_t *wpres; int wtc; int w_exists;
+    const void *tval; const uint8_t *tpres; int ttc;
+    const void *mval; const uint8_t *mpres; int mtc; int has_mask, mask_comp, mask_struct, replace;
+    int accum_op, accum_tc, accum_ztc;   // accum_op < 0: none
+    void *oval; uint8_t *opres;
+};
+__global__ void vec_finalize_kernel(const VecFinalizeArgs a) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool tp = a.tpres ? a.tpres[i] != 0 : true;
+        const bool wp = a.w_exists ? (a.wpres ? a.wpres[i] != 0 : true) : false;
+        bool m = true;
+        if (a.has_mask) {
+            m = a.mpres ? a.mpres[i] != 0 : true;
+            if (m && !a.mask_struct) { const Sc mv = sc_cast(sc_load(a.mtc, a.mval, i), a.mtc, TC_BOOL); m = mv.u != 0; }
+            if (a.mask_comp) m = !m;
+        }
+        Sc out; out.u = 0; bool op = false;
+        if (m) {
+            if (a.accum_op >= 0) {
+                if (wp && tp) {
+                    const Sc x = sc_cast(sc_load(a.wtc, a.wval, i), a.wtc, a.accum_tc);
+                    const Sc y = sc_cast(sc_load(a.ttc, a.tval, i), a.ttc, a.accum_tc);
+                    out = sc_cast(sc_binop(a.accum_op, a.accum_tc, x, y), a.accum_ztc, a.wtc); op = true;
+                } else if (wp) { out = sc_load(a.wtc, a.wval, i); op = true; }
+                else if (tp) { out = sc_cast(sc_load(a.ttc, a.tval, i), a.ttc, a.wtc); op = true; }
+            } else if (tp) { out = sc_cast(sc_load(a.ttc, a.tval, i), a.ttc, a.wtc); op = true; }
+        } else if (!a.replace && wp) { out = sc_load(a.wtc, a.wval, i); op = true; }
+        if (op) sc_store(a.wtc, a.oval, i, out);
+        a.opres[i] = op;
+    }
+}
+
+static inline int grid_for(int64_t n, int threads = 256) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, threads), (int64_t)G.num_sms * 16));
+}
+
+static bool op_uses_x(int op) { return !(op == OP_SECOND || op == OP_PAIR); }
+static bool op_uses_y(int op) { return !(op == OP_FIRST || op == OP_PAIR || op == OP_ANY); }
+
+// w<mask> = accum(w, A' (+).(x) u) with `flip` selecting mul(u,a) (vxm) and `use_transpose`
+// selecting the cached CSR of A' (so that the kernel always pulls along CSR rows).
+static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_Semiring s,
+                         const GrB_Matrix A, const GrB_Vector u, const DescFlags &f, bool use_transpose, bool flip,
+                         const char *fn) {
+    std::string *err = &w->err;
+    // ---- domain / dimension checks (host, synchronous)
+    const GrB_BinaryOp mulop = s->mul; const GrB_BinaryOp addop = s->add->op;
+    if (mulop->opcode == OP_USER || addop->opcode == OP_USER || (accum && accum->opcode == OP_USER))
+        return gb_fail(GrB_INVALID_VALUE, err, "%s: user-defined operators are host function pointers and cannot run on the GPU (no CPU fallback)", fn);
+    const uint64_t out_n = use_transpose ? A->ncols : A->nrows, in_n = use_transpose ? A->nrows : A->ncols;
+    if (u->n != in_n || w->n != out_n || (mask && mask->n != out_n))
+        return gb_fail(GrB_DIMENSION_MISMATCH, err, "%s: dimensions do not match (A is %llux%llu%s, u %llu, w %llu)", fn,
+                       (unsigned long long)A->nrows, (unsigned long long)A->ncols, use_transpose ? " transposed" : "",
+                       (unsigned long long)u->n, (unsigned long long)w->n);
+    if (!G.have_device) return gb_fail(GrB_PANIC, err, "%s: no CUDA device: libb200grb computes only on the GPU (no CPU fallback)", fn);
+    const int xt = mulop->xtype->code, zt = addop->ztype->code;
+    const int add = addop->opcode, mul = mulop->opcode;
+
+    // ---- operands in HBM
+    if (use_transpose) GB_TRY(matrix_ensure_transpose(A)); else GB_TRY(matrix_ensure_device(A));
+    Csr &c = use_transpose ? A->devT : A->dev;
+    GB_TRY(vector_ensure_device(u));
+    if (mask) GB_TRY(vector_ensure_device(mask));
+    const bool need_final = mask != nullptr || accum != nullptr;
+    const bool w_empty = w->host_valid && w->hi.empty() && w->pi.empty();   // nothing to merge with
+    if (need_final && !w_empty) GB_TRY(vector_ensure_device(w));
+    GB_TRY(spmv_plan(c, err));
+
+    const bool a_is_x = !flip;
+    const bool need_a = a_is_x ? op_uses_x(mul) : op_uses_y(mul);
+    const bool need_u = a_is_x ? op_uses_y(mul) : op_uses_x(mul);
+    void *a_cast = nullptr, *u_cast = nullptr;
+    const void *aval = c.val, *uval = u->dval;
+    if (need_a && A->type->code != xt) { GB_TRY(dev_cast_values(&a_cast, xt, c.val, A->type->code, c.nnz, err)); aval = a_cast; }
+    if (need_u && u->type->code != xt) { GB_TRY(dev_cast_values(&u_cast, xt, u->dval, u->type->code, (int64_t)u->n, err)); uval = u_cast; }
+
+    const int64_t n = (int64_t)out_n;
+    const size_t zsz = (size_t)tc_size(zt);
+    void *tval = nullptr; uint8_t *tpres = nullptr;
+    GB_TRY(dmalloc(&tval, (size_t)n * zsz + 16, err));
+    GB_TRY(dmalloc((void **)&tpres, (size_t)n + 16, err));
+
+    if (c.nnz == 0) {
+        clear_presence_kernel<<<grid_for(n), 256, 0, G.stream>>>(tpres, n); GB_LAUNCHED();
+    } else {
+        SpmvArgs a{};
+        a.rowptr = c.rowptr32; a.col = c.col; a.aval = aval; a.tile_row = c.tile_row; a.ntiles = c.ntiles;
+        a.nrows = c.nrows; a.nnz = c.nnz; a.uval = uval; a.upres = u->dpres; a.tval = tval; a.tpres = tpres;
+        a.add_op = add; a.mul_op = mul; a.flip = flip; a.need_a = need_a; a.need_u = need_u;
+        GB_TRY(dmalloc(&a.head_val, (size_t)c.ntiles * zsz + 16, err));
+        GB_TRY(dmalloc(&a.tail_val, (size_t)c.ntiles * zsz + 16, err));
+        GB_TRY(dmalloc((void **)&a.head_has, (size_t)c.ntiles + 16, err));
+        GB_TRY(dmalloc((void **)&a.tail_has, (size_t)c.ntiles + 16, err));
+        GB_TRY(dalloc(&a.tail_row, (size_t)c.ntiles, err));
+        GrB_Info r = spmv_dispatch(xt, zt, add, mul, a, err);
+        dfree(a.head_val); dfree(a.tail_val); dfree(a.head_has); dfree(a.tail_has); dfree(a.tail_row);
+        if (r != GrB_SUCCESS) { dfree(tval); dfree(tpres); dfree(a_cast); dfree(u_cast); return r; }
+    }
+    dfree(a_cast); dfree(u_cast);
+
+    // ---- w<mask> = accum(w, t)
+    const int wtc = w->type->code;
+    if (!need_final) {
+        if (wtc == zt) vector_adopt_device(w, tval, tpres);
+        else {
+            void *cv = nullptr;
+            GB_TRY(dev_cast_values(&cv, wtc, tval, zt, n, err));
+            dfree(tval);
+            vector_adopt_device(w, cv, tpres);
+        }
+    } else {
+        VecFinalizeArgs fa{};
+        fa.n = n; fa.wval = w->dval; fa.wpres = w->dpres; fa.wtc = wtc; fa.w_exists = w_empty ? 0 : 1;
+        fa.tval = tval; fa.tpres = tpres; fa.ttc = zt;
+        if (mask) { fa.mval = mask->dval; fa.mpres = mask->dpres; fa.mtc = mask->type->code; fa.has_mask = 1; }
+        fa.mask_comp = f.mask_comp; fa.mask_struct = f.mask_struct; fa.replace = f.replace;
+        fa.accum_op = accum ? accum->opcode : -1;
+        fa.accum_tc = accum ? accum->xtype->code : 0; fa.accum_ztc = accum ? accum->ztype->code : 0;
+        GB_TRY(dmalloc(&fa.oval, (size_t)n * tc_size(wtc) + 16, err));
+        GB_TRY(dmalloc((void **)&fa.opres, (size_t)n + 16, err));
+        vec_finalize_kernel<<<grid_for(n), 256, 0, G.stream>>>(fa); GB_LAUNCHED();
+        dfree(tval); dfree(tpres);
+        vector_adopt_device(w, fa.oval, fa.opres);
+    }
+    CU_TRY(cudaGetLastError(), err);
+    return GrB_SUCCESS;
+}
+
+static GrB_Info mxv_check(GrB_Vector w, const GrB_Vector mask, const GrB_Semiring s, const GrB_Matrix A, const GrB_Vector u, const char *fn) {
+    if (!w || !s || !A || !u) return gb_fail(GrB_NULL_POINTER, nullptr, "%s: NULL argument", fn);
+    if (!gb_valid_vector(w) || !gb_valid_vector(u) || !gb_valid_matrix(A) || (mask && !gb_valid_vector(mask)) || s->magic != GB_MAGIC)
+        return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "%s: invalid object", fn);
+    return GrB_SUCCESS;
+}
+
+extern "C" GrB_Info GrB_mxv(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_Semiring semiring,
+                            const GrB_Matrix A, const GrB_Vector u, const GrB_Descriptor desc) {
+    GB_LOCK; GB_CHECK_INIT;
+    GB_TRY(mxv_check(w, mask, semiring, A, u, "GrB_mxv"));
+    const DescFlags f = desc_flags(desc);
+    return mxv_core(w, mask, accum, semiring, A, u, f, /*use_transpose=*/f.tran0, /*flip=*/false, "GrB_mxv");
+}
+
+extern "C" GrB_Info GrB_vxm(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_Semiring semiring,
+                            const GrB_Vector u, const GrB_Matrix A, const GrB_Descriptor desc) {
+    GB_LOCK; GB_CHECK_INIT;
+    GB_TRY(mxv_check(w, mask, semiring, A, u, "GrB_vxm"));
+    const DescFlags f = desc_flags(desc);
+    // w' = u'A  <=>  w = A'u: pull along the rows of A' (INP1 = TRAN cancels the transpose)
+    return mxv_core(w, mask, accum, semiring, A, u, f, /*use_transpose=*/!f.tran1, /*flip=*/true, "GrB_vxm");
+}

@@ -1,0 +1,320 @@
+"""Matrix: host-side mirror of /root/reference/pygraphblas/matrix.py for the hot path.
+
+Same names, argument meaning and error behaviour as the reference for
+`Matrix.mxm` (matrix.py:2401-2584), `Matrix.mxv` (matrix.py:2586-2726), `@` / `@=`
+(matrix.py:2728-2737), `**` (matrix.py:1722-1730), `_get_args` (matrix.py:2380-2399)
+and the handle plumbing around them (sparse / from_lists / dup / nvals / to_lists /
+element access / transpose / iseq / wait).  Every numeric operation is one call through
+the C ABI of libb200grb.so (`lib.GrB_mxm`, `lib.GrB_mxv`); nothing is computed in Python.
+"""
+from functools import partial
+import numpy as np
+
+from .base import lib, ffi, NULL, _check, NoValue
+from . import types
+from .ops import current_semiring, current_accum
+from .descriptor import current_desc, T0 as _T0
+
+GxB_INDEX_MAX = 1 << 60
+
+
+class Matrix:
+    __slots__ = ("_matrix", "_keep", "__weakref__")
+
+    def __init__(self, handle):
+        """Wrap a raw GrB_Matrix* (ffi.new("GrB_Matrix*")); the type is read back from the
+        library (matrix.py:99-107)."""
+        self._matrix = handle
+        self._keep = None
+
+    def __del__(self):
+        if lib is not None and getattr(self, "_matrix", None) is not None:
+            lib.GrB_Matrix_free(self._matrix)
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def sparse(cls, typ, nrows=None, ncols=None):
+        """Empty matrix; dimensions default to GxB_INDEX_MAX (matrix.py:120-180)."""
+        nrows = GxB_INDEX_MAX if nrows is None else nrows
+        ncols = GxB_INDEX_MAX if ncols is None else ncols
+        m = ffi.new("GrB_Matrix*")
+        _check(lib.GrB_Matrix_new(m, typ.gb_type, nrows, ncols))
+        return cls(m)
+
+    @classmethod
+    def from_lists(cls, I, J, V=None, nrows=None, ncols=None, typ=None):
+        """Build from coordinate lists; later duplicates win, as with the reference's
+        setElement loop (matrix.py:269-331)."""
+        I = np.ascontiguousarray(I, dtype=np.uint64)
+        J = np.ascontiguousarray(J, dtype=np.uint64)
+        if V is None:
+            V = [True] * len(I)
+            typ = typ or types.BOOL
+        if typ is None:
+            typ = types.from_python(V[0]) if len(V) else types.FP64
+        if nrows is None:
+            nrows = int(I.max()) + 1 if len(I) else 1
+        if ncols is None:
+            ncols = int(J.max()) + 1 if len(J) else 1
+        X = np.ascontiguousarray(V, dtype=typ.dtype)
+        if not (len(I) == len(J) == len(X)):
+            raise ValueError("I, J and V must have the same length")
+        m = cls.sparse(typ, nrows, ncols)
+        _check(typ._Matrix_build(m._matrix[0], ffi.cast("GrB_Index*", I.ctypes.data), ffi.cast("GrB_Index*", J.ctypes.data),
+                                 ffi.cast(typ.ptr, X.ctypes.data), len(I), NULL))
+        return m
+
+    @classmethod
+    def from_csr(cls, indptr, indices, data, nrows, ncols, typ=None):
+        """Bulk CSR ingest straight into HBM (B200 extension `B200_Matrix_import_CSR`; the
+        reference has no bulk build, matrix.py:325).  `data=None` imports the pattern (all 1)."""
+        Ap = np.ascontiguousarray(indptr, dtype=np.int64)
+        Aj = np.ascontiguousarray(indices, dtype=np.uint32)
+        if typ is None:
+            typ = types._dtype_lookup(np.asarray(data).dtype) if data is not None else types.BOOL
+        m = ffi.new("GrB_Matrix*")
+        if data is None:
+            ax = NULL
+        else:
+            Ax = np.ascontiguousarray(data, dtype=typ.dtype)
+            ax = ffi.cast("void*", Ax.ctypes.data)
+        _check(lib.B200_Matrix_import_CSR(m, typ.gb_type, nrows, ncols, ffi.cast("int64_t*", Ap.ctypes.data),
+                                          ffi.cast("uint32_t*", Aj.ctypes.data), ax, len(Aj), 0))
+        return cls(m)
+
+    @classmethod
+    def from_scipy(cls, A, typ=None):
+        A = A.tocsr()
+        A.sort_indices()
+        return cls.from_csr(A.indptr, A.indices, A.data, A.shape[0], A.shape[1], typ)
+
+    def dup(self):
+        m = ffi.new("GrB_Matrix*")
+        _check(lib.GrB_Matrix_dup(m, self._matrix[0]))
+        return Matrix(m)
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def gb_type(self):
+        t = ffi.new("GrB_Type*")
+        _check(lib.GxB_Matrix_type(t, self._matrix[0]))
+        return t[0]
+
+    @property
+    def type(self):
+        return types.from_handle(self.gb_type)
+
+    @property
+    def nrows(self):
+        n = ffi.new("GrB_Index*")
+        _check(lib.GrB_Matrix_nrows(n, self._matrix[0]))
+        return n[0]
+
+    @property
+    def ncols(self):
+        n = ffi.new("GrB_Index*")
+        _check(lib.GrB_Matrix_ncols(n, self._matrix[0]))
+        return n[0]
+
+    @property
+    def shape(self):
+        return (self.nrows, self.ncols)
+
+    @property
+    def nvals(self):
+        n = ffi.new("GrB_Index*")
+        _check(lib.GrB_Matrix_nvals(n, self._matrix[0]))
+        return n[0]
+
+    def __len__(self):
+        return self.nvals
+
+    def clear(self):
+        _check(lib.GrB_Matrix_clear(self._matrix[0]))
+
+    def wait(self):
+        """Force completion of pending work (matrix.py:3348-3353)."""
+        _check(lib.GrB_Matrix_wait(self._matrix))
+
+    # ------------------------------------------------------------------ element access
+    def to_arrays(self):
+        """(I, J, X) numpy arrays in row-major order (matrix.py:1475-1492)."""
+        typ = self.type
+        n = self.nvals
+        I = np.empty(n, np.uint64)
+        J = np.empty(n, np.uint64)
+        X = np.empty(n, typ.dtype)
+        nv = ffi.new("GrB_Index*", n)
+        _check(typ._Matrix_extractTuples(ffi.cast("GrB_Index*", I.ctypes.data), ffi.cast("GrB_Index*", J.ctypes.data),
+                                         ffi.cast(typ.ptr, X.ctypes.data), nv, self._matrix[0]))
+        return I, J, X
+
+    def to_lists(self):
+        I, J, X = self.to_arrays()
+        return [I.tolist(), J.tolist(), X.tolist()]
+
+    def __iter__(self):
+        I, J, X = self.to_lists()
+        return iter(zip(I, J, X))
+
+    def to_csr(self):
+        """(indptr int64, indices uint32, data) numpy arrays (B200 extension)."""
+        typ = self.type
+        n = self.nvals
+        Ap = np.empty(self.nrows + 1, np.int64)
+        Aj = np.empty(n, np.uint32)
+        Ax = np.empty(n, typ.dtype)
+        _check(lib.B200_Matrix_export_CSR(self._matrix[0], ffi.cast("int64_t*", Ap.ctypes.data),
+                                          ffi.cast("uint32_t*", Aj.ctypes.data), ffi.cast("void*", Ax.ctypes.data), 0))
+        return Ap, Aj, Ax
+
+    def __getitem__(self, index):
+        i, j = index
+        typ = self.type
+        x = ffi.new(typ.ptr)
+        res = typ._Matrix_extractElement(x, self._matrix[0], i, j)
+        if res == lib.GrB_NO_VALUE:
+            raise NoValue(f"no value at ({i},{j})")
+        _check(res)
+        return typ.from_value(x[0])
+
+    def get(self, i, j, default=None):
+        try:
+            return self[i, j]
+        except NoValue:
+            return default
+
+    def __setitem__(self, index, value):
+        i, j = index
+        typ = self.type
+        _check(typ._Matrix_setElement(self._matrix[0], typ.from_value(value), i, j))
+
+    def __delitem__(self, index):
+        i, j = index
+        _check(lib.GrB_Matrix_removeElement(self._matrix[0], i, j))
+
+    def __contains__(self, index):
+        return self.get(*index) is not None
+
+    def iseq(self, other):
+        """Same type, shape, pattern and values (matrix.py:1436-1453)."""
+        if not isinstance(other, Matrix) or self.type is not other.type or self.shape != other.shape:
+            return False
+        a, b = self.to_arrays(), other.to_arrays()
+        return all(np.array_equal(x, y) for x, y in zip(a, b))
+
+    def isne(self, other):
+        return not self.iseq(other)
+
+    def transpose(self, cast=None, out=None, mask=None, accum=None, desc=None):
+        """New matrix holding the transpose (matrix.py:1003-1061)."""
+        if out is None:
+            out = Matrix.sparse(cast or self.type, self.ncols, self.nrows)
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(lib.GrB_transpose(out._matrix[0], mask, accum, self._matrix[0], desc))
+        return out
+
+    @property
+    def T(self):
+        return self.transpose()
+
+    # ------------------------------------------------------------------ the hot path
+    def _get_args(self, mask=None, accum=None, desc=None):
+        """Resolve mask handle, accumulator and descriptor incl. the context-manager
+        defaults (matrix.py:2380-2399)."""
+        from .vector import Vector
+        if isinstance(mask, Matrix):
+            mask = mask._matrix[0]
+        elif isinstance(mask, Vector):
+            mask = mask._vector[0]
+        else:
+            mask = NULL
+        if accum is None:
+            accum = current_accum.get(NULL)
+        if accum is not NULL:
+            accum = accum.get_op()
+        if desc is None:
+            desc = current_desc.get(NULL)
+        if desc is not NULL:
+            desc = desc.get_desc()
+        return mask, accum, desc
+
+    def mxm(self, other, semiring=None, cast=None, out=None, mask=None, accum=None, desc=None):
+        """Matrix-matrix multiply C<mask> = accum(C, A (+).(x) B)  (matrix.py:2401-2584)."""
+        if not isinstance(other, Matrix):
+            raise TypeError("Right argument to mxm must be a Matrix.")
+        if semiring is None:
+            semiring = current_semiring.get(NULL)
+        if out is None:
+            if cast is not None:
+                typ = cast
+            elif semiring is not NULL:
+                typ = semiring.ztype
+            else:
+                typ = types.promote(self.type, other.type)
+            out = Matrix.sparse(typ, self.nrows, other.ncols)      # matrix.py:2563 (ignores T0/T1)
+        else:
+            typ = out.type
+        if semiring is NULL:
+            semiring = out.type._default_semiring()
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(lib.GrB_mxm(out._matrix[0], mask, accum, semiring.get_op(), self._matrix[0], other._matrix[0], desc))
+        return out
+
+    def mxv(self, other, semiring=None, cast=None, out=None, mask=None, accum=None, desc=None):
+        """Matrix-vector multiply w<mask> = accum(w, A (+).(x) u)  (matrix.py:2586-2726)."""
+        from .vector import Vector
+        if not isinstance(other, Vector):
+            raise TypeError("Right argument to mxv must be a Vector.")
+        if semiring is None:
+            semiring = current_semiring.get(NULL)
+        if out is None:
+            d = desc if desc is not None else current_desc.get(None)
+            new_dimension = self.ncols if (d is not None and _T0 in d) else self.nrows
+            if cast is not None:
+                typ = cast
+            elif semiring is not NULL:
+                typ = semiring.ztype
+            else:
+                typ = types.promote(self.type, other.type)
+            out = Vector.sparse(typ, new_dimension)
+        if semiring is NULL:
+            semiring = out.type._default_semiring()
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(lib.GrB_mxv(out._vector[0], mask, accum, semiring.get_op(), self._matrix[0], other._vector[0], desc))
+        return out
+
+    def __matmul__(self, other):
+        from .vector import Vector
+        if isinstance(other, Matrix):
+            return self.mxm(other)
+        if isinstance(other, Vector):
+            return self.mxv(other)
+        raise TypeError("Right argument to @ must be Matrix or Vector.")
+
+    def __imatmul__(self, other):
+        return self.mxm(other, out=self)
+
+    def __pow__(self, exponent):
+        """A ** k by repeated mxm into a copy (matrix.py:1722-1730)."""
+        if exponent == 0:
+            raise ValueError("exponent must be >= 1")
+        if exponent == 1:
+            return self.dup()
+        result = self.dup()
+        for _ in range(1, exponent):
+            result.mxm(self, out=result)
+        return result
+
+    def __getattr__(self, name):
+        """`A.min_plus(B)`: look the operator up on the type (matrix.py:1607-1613)."""
+        if name.startswith("_"):
+            raise AttributeError(name)
+        try:
+            attr = getattr(self.type, name)
+        except AttributeError:
+            raise AttributeError(f"Matrix has no attribute or type operator {name}")
+        return partial(attr, self)
+
+    def __repr__(self):
+        return f"<Matrix ({self.nrows}x{self.ncols} : {self.nvals}:{self.type.name})>"
