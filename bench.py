@@ -284,6 +284,15 @@ def run_b200(args):
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg_bytes,
                 "kernel_ms": kms, "peak_source": peak_src}
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "ms_per_step": ms, "roofline": roofline,
+                              "gpu_launches": int(launches), "clocks": clocks, "quick": True}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     # ---- end to end through the public API with host buffers: H2D u, mxv, D2H w (+ presence)
     u_pin = torch.empty(n, dtype=torch.float32).pin_memory().numpy()
     u_pin[:] = u_host0
@@ -406,6 +415,7 @@ def main():
     ap.add_argument("--spgemm-scale", type=int, default=20)
     ap.add_argument("--no-spgemm", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--quick", action="store_true", help="timed SpMV loop only (for ncu): no e2e / CPU baseline / SpGEMM")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

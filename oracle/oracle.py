@@ -20,7 +20,19 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_BUILD = os.path.join(_HERE, "_build")
+def _cpu_tag():
+    """Builds are keyed by the host CPU's feature flags: a -march=native library must not be
+    carried to a different machine (the GPU box) and executed there."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((ln for ln in f if ln.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    return hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
+_BUILD = os.path.join(_HERE, "_build", _cpu_tag())
 _LIB = os.path.join(_BUILD, "liboracle.so")
 _SOURCES = [os.path.join(_HERE, "grb_oracle.c"), os.path.join(_HERE, "grb_fast.c")]
 

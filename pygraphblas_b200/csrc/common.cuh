@@ -301,7 +301,7 @@ template <typename T> __host__ __device__ __forceinline__ T op_apply(int op, T x
     switch (op) {
         case OP_FIRST:  return x;
         case OP_SECOND: return y;
-        case OP_ANY:    return x;
+        case OP_ANY:    return y;
         case OP_PAIR:   return (T)1;
         case OP_MIN:    if (F) return (T)fmin((double)x, (double)y); return x < y ? x : y;
         case OP_MAX:    if (F) return (T)fmax((double)x, (double)y); return x > y ? x : y;
@@ -330,8 +330,8 @@ template <typename T> __host__ __device__ __forceinline__ T op_apply(int op, T x
 }
 template <> __host__ __device__ __forceinline__ float op_apply<float>(int op, float x, float y) {
     switch (op) {
-        case OP_FIRST: case OP_ANY: return x;
-        case OP_SECOND: return y;
+        case OP_FIRST: return x;
+        case OP_SECOND: case OP_ANY: return y;
         case OP_PAIR:   return 1.0f;
         case OP_MIN:    return fminf(x, y);
         case OP_MAX:    return fmaxf(x, y);
@@ -357,8 +357,8 @@ template <> __host__ __device__ __forceinline__ float op_apply<float>(int op, fl
 // BOOL: arithmetic names alias logical ones (PLUS=LOR, TIMES=LAND, MIN=LAND, MAX=LOR, MINUS=LXOR, DIV=FIRST ...)
 template <> __host__ __device__ __forceinline__ bool op_apply<bool>(int op, bool x, bool y) {
     switch (op) {
-        case OP_FIRST: case OP_ANY: case OP_DIV: return x;
-        case OP_SECOND: case OP_RDIV: return y;
+        case OP_FIRST: case OP_DIV: return x;
+        case OP_SECOND: case OP_RDIV: case OP_ANY: return y;
         case OP_PAIR:   return true;
         case OP_MIN: case OP_TIMES: case OP_LAND: return x && y;
         case OP_MAX: case OP_PLUS: case OP_LOR: return x || y;

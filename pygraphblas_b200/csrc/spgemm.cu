@@ -373,17 +373,53 @@ template <typename W> __global__ void fill_words_kernel(W *a, W v, int64_t n) {
 }
 
 // ------------------------------------------------------------------ masked: shared-memory hash of the mask row
-// keys[s] = column, slot[s] = position inside the mask row; vals / found are indexed by that position.
+// Work unit = a "chunk": (row i, a slice of A(i,:)) whose flop count is bounded, so that hub rows are
+// spread over many CTAs.  Every chunk hashes the mask row M(i,:) (keys -> position inside the row),
+// then streams the B rows named by its slice of A(i,:) and accumulates products that hit the mask.
+// A warp handles 32 A entries at a time: each lane fetches one (k, B row range) up front, the ranges
+// are broadcast by shuffle and the lanes stride the B row -- the dependent-load chain per A entry
+// is paid once per 32 entries.
+struct MaskedArgs {
+    GemmArgs g;
+    const int32_t *chunk_row; const uint32_t *chunk_idx; const uint32_t *chunk_cnt; int64_t nchunks;
+    void *t_words;     // nnz(M) accumulator words (pre-set to the monoid identity)
+};
+
+template <typename XT, typename ZT, typename Hit>
+__device__ __forceinline__ void stream_b_rows(const GemmArgs &p, uint32_t pa0, uint32_t pa1, int lane, Hit &&hit) {
+    const XT *aval = static_cast<const XT *>(p.a_val);
+    for (uint32_t base = pa0; base < pa1; base += 32) {
+        const uint32_t pa = base + lane;
+        const bool valid = pa < pa1;
+        const uint32_t k = valid ? __ldg(p.a_col + pa) : 0u;
+        const uint32_t bs = valid ? __ldg(p.b_ptr + k) : 0u, be = valid ? __ldg(p.b_ptr + k + 1) : 0u;
+        XT av = (XT)1;
+        if (p.need_a && valid) av = gload<XT>(aval + pa);
+        const int cnt = min(32u, pa1 - base);
+        for (int l = 0; l < cnt; ++l) {
+            const uint32_t s = __shfl_sync(0xffffffffu, bs, l), e = __shfl_sync(0xffffffffu, be, l);
+            XT a;
+            if constexpr (sizeof(XT) == 8) { long long t = __shfl_sync(0xffffffffu, reinterpret_cast<long long &>(av), l); a = reinterpret_cast<XT &>(t); }
+            else if constexpr (sizeof(XT) == 4) { int t = __shfl_sync(0xffffffffu, reinterpret_cast<int &>(av), l); a = reinterpret_cast<XT &>(t); }
+            else { int t = __shfl_sync(0xffffffffu, (int)av, l); a = (XT)t; }
+            for (uint32_t pb = s + lane; pb < e; pb += 32) hit(__ldg(p.b_col + pb), a, pb);
+        }
+    }
+}
+
 template <typename XT, typename ZT, int ADD, int MUL, bool WARP>
-__global__ void __launch_bounds__(256) masked_hash_kernel(const GemmArgs p) {
+__global__ void __launch_bounds__(256) masked_hash_kernel(const MaskedArgs ma) {
     typedef typename SlotWord<ZT>::W W;
+    const GemmArgs &p = ma.g;
     extern __shared__ unsigned char smem_raw[];
+    __shared__ unsigned int s_next;
     const int add = ADD >= 0 ? ADD : p.add_op;
     const int mul = MUL >= 0 ? MUL : p.mul_op;
     const int gsize = WARP ? 32 : blockDim.x;
     const int gid = WARP ? (threadIdx.x >> 5) : 0;
     const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x;
     const int groups = WARP ? (blockDim.x >> 5) : 1;
+    const int lane = threadIdx.x & 31;
     const int half = p.table >> 1;                                    // max mask-row length
     // layout per group: keys[table] u32 | slot[table] u32 | vals[half] W | found[half] u8
     const size_t per_group = (size_t)p.table * 8 + (size_t)half * sizeof(W) + (size_t)half;
@@ -393,15 +429,21 @@ __global__ void __launch_bounds__(256) masked_hash_kernel(const GemmArgs p) {
     W *vals = reinterpret_cast<W *>(slot + p.table);
     uint8_t *found = reinterpret_cast<uint8_t *>(vals + half);
     const int64_t idx = (int64_t)blockIdx.x * groups + gid;
-    const bool active = idx < p.nbin;
+    const bool active = WARP ? idx < p.nbin : idx < ma.nchunks;
     const uint32_t tmask = (uint32_t)p.table - 1;
     const W ident = pack_slot<ZT>(monoid_identity<ZT>(add));
-    for (int s = tid; s < p.table; s += gsize) keys[s] = EMPTY_KEY;
-    for (int s = tid; s < half; s += gsize) { vals[s] = ident; found[s] = 0; }
-    group_sync<WARP>();
-    int64_t row = 0; uint32_t ms = 0, me = 0;
+    int64_t row = 0; uint32_t ms = 0, me = 0, nparts = 1, part = 0;
     if (active) {
-        row = p.rows[idx]; ms = p.m_ptr[row]; me = p.m_ptr[row + 1];
+        if (WARP) row = p.rows[idx];
+        else { row = ma.chunk_row[idx]; part = ma.chunk_idx[idx]; nparts = ma.chunk_cnt[idx]; }
+        ms = p.m_ptr[row]; me = p.m_ptr[row + 1];
+    }
+    const int mlen = (int)(me - ms);
+    for (int s = tid; s < p.table; s += gsize) keys[s] = EMPTY_KEY;
+    for (int s = tid; s < mlen; s += gsize) { vals[s] = ident; found[s] = 0; }
+    if (!WARP && threadIdx.x == 0) s_next = 0;
+    group_sync<WARP>();
+    if (active) {
         for (uint32_t q = ms + tid; q < me; q += gsize) {
             bool on = true;
             if (!p.m_struct) on = sc_cast(sc_load(p.m_tc, p.m_val, q), p.m_tc, TC_BOOL).u != 0;
@@ -414,8 +456,7 @@ __global__ void __launch_bounds__(256) masked_hash_kernel(const GemmArgs p) {
     }
     group_sync<WARP>();
     if (active) {
-        const XT *aval = static_cast<const XT *>(p.a_val), *bval = static_cast<const XT *>(p.b_val);
-        const uint32_t as = p.a_ptr[row], ae = p.a_ptr[row + 1];
+        const XT *bval = static_cast<const XT *>(p.b_val);
         auto hit = [&](uint32_t j, XT av, uint32_t pb) {
             uint32_t s = hash_col(j, tmask);
             while (true) {
@@ -431,71 +472,108 @@ __global__ void __launch_bounds__(256) masked_hash_kernel(const GemmArgs p) {
                 s = (s + 1) & tmask;
             }
         };
-        if (WARP) {
-            for (uint32_t pa = as + tid; pa < ae; pa += 32) {
-                const uint32_t k = p.a_col[pa];
-                const XT av = p.need_a ? gload<XT>(aval + pa) : (XT)1;
-                for (uint32_t pb = p.b_ptr[k]; pb < p.b_ptr[k + 1]; ++pb) hit(__ldg(p.b_col + pb), av, pb);
-            }
-        } else {
-            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-            for (uint32_t pa = as + warp; pa < ae; pa += nwarps) {
-                const uint32_t k = p.a_col[pa];
-                const XT av = p.need_a ? gload<XT>(aval + pa) : (XT)1;
-                for (uint32_t pb = p.b_ptr[k] + lane; pb < p.b_ptr[k + 1]; pb += 32) hit(__ldg(p.b_col + pb), av, pb);
+        const uint32_t as = p.a_ptr[row], ae = p.a_ptr[row + 1];
+        if (WARP) stream_b_rows<XT, ZT>(p, as, ae, lane, hit);
+        else {
+            // this chunk's slice of A(i,:), handed to the warps 32 entries at a time
+            const uint32_t alen = ae - as;
+            const uint32_t c0 = as + (uint32_t)(((uint64_t)alen * part) / nparts), c1 = as + (uint32_t)(((uint64_t)alen * (part + 1)) / nparts);
+            while (true) {
+                uint32_t b = 0;
+                if (lane == 0) b = atomicAdd(&s_next, 32u);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                if (c0 + b >= c1) break;
+                stream_b_rows<XT, ZT>(p, c0 + b, min(c0 + b + 32u, c1), lane, hit);
             }
         }
     }
     group_sync<WARP>();
     if (active) {
-        ZT *tval = static_cast<ZT *>(p.c_val);
-        for (uint32_t q = tid; q < me - ms; q += gsize) { tval[ms + q] = unpack_slot<ZT>(vals[q]); p.t_found[ms + q] = found[q]; }
+        W *tw = static_cast<W *>(ma.t_words);
+        if (nparts == 1) {
+            for (int q = tid; q < mlen; q += gsize) { tw[ms + q] = vals[q]; p.t_found[ms + q] = found[q]; }
+        } else {
+            for (int q = tid; q < mlen; q += gsize) if (found[q]) {
+                atomic_combine<ZT>(&tw[ms + q], unpack_slot<ZT>(vals[q]), add);
+                p.t_found[ms + q] = 1;
+            }
+        }
     }
 }
 
-// masked, long mask rows: a dense column -> mask-position map in HBM owned by a persistent CTA
+// masked, long mask rows: a dense column -> mask-position map in HBM owned by a persistent CTA;
+// chunks come from a queue and accumulate straight into the global accumulator words.
 template <typename XT, typename ZT, int ADD, int MUL>
-__global__ void __launch_bounds__(512) masked_spa_kernel(const GemmArgs p) {
+__global__ void __launch_bounds__(512) masked_spa_kernel(const MaskedArgs ma) {
     typedef typename SlotWord<ZT>::W W;
-    __shared__ unsigned int s_next;
+    const GemmArgs &p = ma.g;
+    __shared__ unsigned int s_next, s_sub;
     const int add = ADD >= 0 ? ADD : p.add_op;
     const int mul = MUL >= 0 ? MUL : p.mul_op;
     int32_t *slot = p.spa_slot + (size_t)blockIdx.x * p.ncols;      // -1 everywhere when idle
-    const XT *aval = static_cast<const XT *>(p.a_val), *bval = static_cast<const XT *>(p.b_val);
-    W *tval = static_cast<W *>(p.spa_val);                          // nnz(M) accumulator words
-    const W ident = pack_slot<ZT>(monoid_identity<ZT>(add));
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const XT *bval = static_cast<const XT *>(p.b_val);
+    W *tw = static_cast<W *>(ma.t_words);
+    const int lane = threadIdx.x & 31;
     while (true) {
-        if (threadIdx.x == 0) s_next = atomicAdd(p.queue, 1u);
+        if (threadIdx.x == 0) { s_next = atomicAdd(p.queue, 1u); s_sub = 0; }
         __syncthreads();
         const unsigned int idx = s_next;
-        __syncthreads();
-        if (idx >= p.nbin) break;
-        const int64_t row = p.rows[idx];
+        if (idx >= ma.nchunks) break;
+        const int64_t row = ma.chunk_row[idx];
+        const uint32_t part = ma.chunk_idx[idx], nparts = ma.chunk_cnt[idx];
         const uint32_t ms = p.m_ptr[row], me = p.m_ptr[row + 1];
         for (uint32_t q = ms + threadIdx.x; q < me; q += blockDim.x) {
             bool on = true;
             if (!p.m_struct) on = sc_cast(sc_load(p.m_tc, p.m_val, q), p.m_tc, TC_BOOL).u != 0;
-            tval[q] = ident; p.t_found[q] = 0;
             if (on) slot[p.m_col[q]] = (int32_t)q;
         }
         __syncthreads();
-        const uint32_t as = p.a_ptr[row], ae = p.a_ptr[row + 1];
-        for (uint32_t pa = as + warp; pa < ae; pa += nwarps) {
-            const uint32_t k = p.a_col[pa];
-            const XT av = p.need_a ? gload<XT>(aval + pa) : (XT)1;
-            for (uint32_t pb = p.b_ptr[k] + lane; pb < p.b_ptr[k + 1]; pb += 32) {
-                const int32_t q = slot[__ldg(p.b_col + pb)];
-                if (q >= 0) {
-                    const XT bv = p.need_b ? gload<XT>(bval + pb) : (XT)1;
-                    atomic_combine<ZT>(&tval[q], MulApply<XT, ZT>::f(mul, av, bv), add);
-                    p.t_found[q] = 1;
-                }
+        auto hit = [&](uint32_t j, XT av, uint32_t pb) {
+            const int32_t q = slot[j];
+            if (q >= 0) {
+                const XT bv = p.need_b ? gload<XT>(bval + pb) : (XT)1;
+                atomic_combine<ZT>(&tw[q], MulApply<XT, ZT>::f(mul, av, bv), add);
+                p.t_found[q] = 1;
             }
+        };
+        const uint32_t as = p.a_ptr[row], ae = p.a_ptr[row + 1], alen = ae - as;
+        const uint32_t c0 = as + (uint32_t)(((uint64_t)alen * part) / nparts), c1 = as + (uint32_t)(((uint64_t)alen * (part + 1)) / nparts);
+        while (true) {
+            uint32_t b = 0;
+            if (lane == 0) b = atomicAdd(&s_sub, 32u);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (c0 + b >= c1) break;
+            stream_b_rows<XT, ZT>(p, c0 + b, min(c0 + b + 32u, c1), lane, hit);
         }
         __syncthreads();
         for (uint32_t q = ms + threadIdx.x; q < me; q += blockDim.x) slot[p.m_col[q]] = -1;
         __syncthreads();
+    }
+}
+
+// per-row chunk counts: class 1 rows (warp kernel) get 0 chunks
+__global__ void chunk_count_kernel(const int64_t *flops, const uint32_t *m_ptr, int64_t nrows, int64_t chunk_flops,
+                                   int warp_flops, int warp_mlen, int medium_mlen, int64_t *cnt_medium, int64_t *cnt_long, int64_t *cls1) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = flops[r]; const int64_t ml = m_ptr[r + 1] - m_ptr[r];
+        int64_t cm = 0, cl = 0, c1 = 0;
+        if (f > 0 && ml > 0) {
+            if (f <= warp_flops && ml <= warp_mlen) c1 = 1;
+            else if (ml <= medium_mlen) cm = (f + chunk_flops - 1) / chunk_flops;
+            else cl = (f + chunk_flops - 1) / chunk_flops;
+        }
+        cnt_medium[r] = cm; cnt_long[r] = cl; cls1[r] = c1;
+    }
+}
+// after exclusive scans of the three arrays: emit the chunk lists and the class-1 row list
+__global__ void chunk_fill_kernel(const int64_t *off_medium, const int64_t *off_long, const int64_t *off_cls1, int64_t nrows,
+                                  int32_t *m_row, uint32_t *m_idx, uint32_t *m_cnt,
+                                  int32_t *l_row, uint32_t *l_idx, uint32_t *l_cnt, int32_t *w_rows) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t cm = off_medium[r + 1] - off_medium[r], cl = off_long[r + 1] - off_long[r];
+        for (int64_t c = 0; c < cm; ++c) { const int64_t o = off_medium[r] + c; m_row[o] = (int32_t)r; m_idx[o] = (uint32_t)c; m_cnt[o] = (uint32_t)cm; }
+        for (int64_t c = 0; c < cl; ++c) { const int64_t o = off_long[r] + c; l_row[o] = (int32_t)r; l_idx[o] = (uint32_t)c; l_cnt[o] = (uint32_t)cl; }
+        if (off_cls1[r + 1] > off_cls1[r]) w_rows[off_cls1[r]] = (int32_t)r;
     }
 }
 
@@ -504,16 +582,10 @@ template <typename ZT> static void spa_fill_identity(void *words, int64_t n, int
     fill_words_kernel<W><<<grid_for(n), 256, 0, G.stream>>>(static_cast<W *>(words), pack_slot<ZT>(monoid_identity<ZT>(add)), n);
 }
 
-// accumulator words (32-bit) -> 1- or 2-byte typed values, for the mask rows of one bin
-__global__ void unpack_rows_kernel(const int32_t *rows, int64_t nbin, const uint32_t *m_ptr, const uint32_t *words, uint8_t *out, int vsize) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t k = warp; k < nbin; k += nwarps) {
-        const int64_t r = rows[k];
-        for (uint32_t q = m_ptr[r] + lane; q < m_ptr[r + 1]; q += 32) {
-            if (vsize == 1) out[q] = (uint8_t)words[q]; else ((uint16_t *)out)[q] = (uint16_t)words[q];
-        }
+// accumulator words (32-bit) -> 1- or 2-byte typed values
+__global__ void narrow_words_kernel(const uint32_t *words, uint8_t *out, int vsize, int64_t n) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        if (vsize == 1) out[q] = (uint8_t)words[q]; else ((uint16_t *)out)[q] = (uint16_t)words[q];
     }
 }
 __global__ void row_len_kernel(const uint32_t *ptr, int64_t n, int64_t *out) {
@@ -546,7 +618,8 @@ __global__ void __launch_bounds__(256) masked_dot_kernel(const GemmArgs p) {
                     if (cx == cy) {
                         const XT av = p.need_a ? gload<XT>(aval + x) : (XT)1;
                         const XT bv = p.need_b ? gload<XT>(bval + y) : (XT)1;
-                        acc = MulApply<ZT, ZT>::f(add, acc, MulApply<XT, ZT>::f(mul, av, bv));
+                        const ZT prod = MulApply<XT, ZT>::f(mul, av, bv);
+                        acc = has ? MulApply<ZT, ZT>::f(add, acc, prod) : prod;
                         has = 1; ++x; ++y;
                     } else if (cx < cy) ++x; else ++y;
                 }
@@ -808,78 +881,90 @@ static GrB_Info spgemm_unmasked(const Csr &A, const Csr &B, const void *aval, co
 
 // T<M> = A (+).(x) B restricted to a non-complemented mask M (pattern of T is a subset of M's).
 // dot == true computes A (+).(x) B' by row intersections instead (B given un-transposed).
+static constexpr int64_t CHUNK_FLOPS = 32768;     // flop budget of one CTA-level work unit
+static constexpr int WARP_FLOPS = 2048;           // rows at most this heavy (and with short mask rows) run warp-per-row
+
 static GrB_Info spgemm_masked(const Csr &A, const Csr &B, const void *aval, const void *bval, int xt, int zt,
                               int add, int mul, bool need_a, bool need_b, const Csr &M, int mtc, bool m_struct,
                               bool dot, Csr &T, std::string *err) {
     const int64_t nrows = A.nrows, ncols = dot ? B.nrows : B.ncols;
     T = Csr(); T.nrows = nrows; T.ncols = ncols;
     const size_t zsz = (size_t)tc_size(zt), wsize = zsz == 8 ? 8 : 4;
-    GemmArgs g{};
+    MaskedArgs ma{};
+    GemmArgs &g = ma.g;
     g.a_ptr = A.rowptr32; g.a_col = A.col; g.a_val = aval; g.b_ptr = B.rowptr32; g.b_col = B.col; g.b_val = bval;
     g.m_ptr = M.rowptr32; g.m_col = M.col; g.m_val = M.val; g.m_tc = mtc; g.m_struct = m_struct;
     g.nrows = nrows; g.ncols = ncols; g.add_op = add; g.mul_op = mul; g.need_a = need_a; g.need_b = need_b;
-    void *tval = nullptr; uint8_t *found = nullptr;
-    GB_TRY(dmalloc(&tval, (size_t)M.nnz * zsz + 16, err));
+    void *words = nullptr; uint8_t *found = nullptr;          // per mask entry: accumulator word, "has a value"
+    GB_TRY(dmalloc(&words, (size_t)M.nnz * wsize + 16, err));
     GB_TRY(dmalloc((void **)&found, (size_t)M.nnz + 16, err));
-    g.c_val = tval; g.t_found = found;
+    g.c_val = words; g.t_found = found; ma.t_words = words;
     G.last_flops = 0;
-    if (!dot) {   // flop statistics (number of multiplies an unmasked Gustavson pass would do)
+    if (M.nnz > 0 && dot) {
+        // the dot kernel writes typed values directly
+#define K_DOT(XT, ZT, A_, M_) masked_dot_kernel<XT, ZT, A_, M_><<<grid_for(nrows * 32), 256, 0, G.stream>>>(g)
+        GB_FOR_SEMIRING(xt, zt, add, mul, K_DOT, err); GB_LAUNCHED();
+    } else if (M.nnz > 0) {
         int64_t *flops = nullptr; unsigned long long *total = nullptr;
         GB_TRY(dalloc(&flops, (size_t)nrows, err)); GB_TRY(dalloc(&total, 1, err));
         CU_TRY(cudaMemsetAsync(total, 0, 8, G.stream), err);
         flops_kernel<<<grid_for(nrows * 32), 256, 0, G.stream>>>(A.rowptr32, A.col, B.rowptr32, nrows, flops, total); GB_LAUNCHED();
-        int64_t tf = 0; GB_TRY(read_i64((const int64_t *)total, &tf, err));
+        // accumulators start at the identity, flags at 0
+        CU_TRY(cudaMemsetAsync(found, 0, (size_t)M.nnz, G.stream), err);
+#define K_IDENT(XT, ZT, A_, M_) spa_fill_identity<ZT>(words, M.nnz, (A_) >= 0 ? (A_) : add)
+        GB_FOR_SEMIRING(xt, zt, add, mul, K_IDENT, err); GB_LAUNCHED();
+        // classify rows and cut heavy ones into flop-bounded chunks
+        int64_t *cm = nullptr, *cl = nullptr, *c1 = nullptr;
+        GB_TRY(dalloc(&cm, (size_t)nrows + 1, err)); GB_TRY(dalloc(&cl, (size_t)nrows + 1, err)); GB_TRY(dalloc(&c1, (size_t)nrows + 1, err));
+        CU_TRY(cudaMemsetAsync(cm + nrows, 0, 8, G.stream), err); CU_TRY(cudaMemsetAsync(cl + nrows, 0, 8, G.stream), err);
+        CU_TRY(cudaMemsetAsync(c1 + nrows, 0, 8, G.stream), err);
+        chunk_count_kernel<<<grid_for(nrows), 256, 0, G.stream>>>(flops, M.rowptr32, nrows, CHUNK_FLOPS, WARP_FLOPS, SMALL_TABLE / 2,
+                                                                  MEDIUM_TABLE / 2, cm, cl, c1); GB_LAUNCHED();
+        GB_TRY(dev_exclusive_scan(cm, nrows + 1, err)); GB_TRY(dev_exclusive_scan(cl, nrows + 1, err)); GB_TRY(dev_exclusive_scan(c1, nrows + 1, err));
+        int64_t n_medium = 0, n_long = 0, n_warp = 0, tf = 0;
+        GB_TRY(read_i64(cm + nrows, &n_medium, err)); GB_TRY(read_i64(cl + nrows, &n_long, err)); GB_TRY(read_i64(c1 + nrows, &n_warp, err));
+        GB_TRY(read_i64((const int64_t *)total, &tf, err));
         G.last_flops = (uint64_t)tf;
-        dfree(flops); dfree(total);
-    }
-    if (M.nnz > 0) {
-        if (dot) {
-#define K_DOT(XT, ZT, A_, M_) masked_dot_kernel<XT, ZT, A_, M_><<<grid_for(nrows * 32), 256, 0, G.stream>>>(g)
-            GB_FOR_SEMIRING(xt, zt, add, mul, K_DOT, err); GB_LAUNCHED();
-        } else {
-            // bin rows by mask-row length (the table holds the mask row at load factor <= 1/2)
-            int64_t *mlen = nullptr;
-            GB_TRY(dalloc(&mlen, (size_t)nrows + 1, err));
-            row_len_kernel<<<grid_for(nrows), 256, 0, G.stream>>>(M.rowptr32, nrows, mlen); GB_LAUNCHED();
-            RowBins bins;
-            GB_TRY(make_bins(mlen, nrows, BinLimits{SMALL_TABLE / 2, MEDIUM_TABLE / 2}, bins, err));
-            dfree(mlen);
-            if (bins.count[1]) {
-                g.rows = bins.rows + bins.offset[1]; g.nbin = bins.count[1]; g.table = SMALL_TABLE;
-                const size_t sm = masked_smem(SMALL_TABLE, 8, wsize);
-#define K_MSMALL(XT, ZT, A_, M_) masked_hash_kernel<XT, ZT, A_, M_, true><<<(unsigned)ceil_div(g.nbin, 8), 256, sm, G.stream>>>(g)
-                GB_FOR_SEMIRING(xt, zt, add, mul, K_MSMALL, err); GB_LAUNCHED();
-            }
-            if (bins.count[2]) {
-                g.rows = bins.rows + bins.offset[2]; g.nbin = bins.count[2]; g.table = MEDIUM_TABLE;
-                const size_t sm = masked_smem(MEDIUM_TABLE, 1, wsize);
+        int32_t *m_row = nullptr, *l_row = nullptr, *w_rows = nullptr; uint32_t *m_idx = nullptr, *m_cnt = nullptr, *l_idx = nullptr, *l_cnt = nullptr;
+        GB_TRY(dalloc(&m_row, (size_t)n_medium, err)); GB_TRY(dalloc(&m_idx, (size_t)n_medium, err)); GB_TRY(dalloc(&m_cnt, (size_t)n_medium, err));
+        GB_TRY(dalloc(&l_row, (size_t)n_long, err)); GB_TRY(dalloc(&l_idx, (size_t)n_long, err)); GB_TRY(dalloc(&l_cnt, (size_t)n_long, err));
+        GB_TRY(dalloc(&w_rows, (size_t)n_warp, err));
+        chunk_fill_kernel<<<grid_for(nrows), 256, 0, G.stream>>>(cm, cl, c1, nrows, m_row, m_idx, m_cnt, l_row, l_idx, l_cnt, w_rows); GB_LAUNCHED();
+        dfree(flops); dfree(total); dfree(cm); dfree(cl); dfree(c1);
+        if (n_warp) {
+            g.rows = w_rows; g.nbin = n_warp; g.table = SMALL_TABLE;
+            const size_t sm = masked_smem(SMALL_TABLE, 8, wsize);
+#define K_MSMALL(XT, ZT, A_, M_) masked_hash_kernel<XT, ZT, A_, M_, true><<<(unsigned)ceil_div(n_warp, 8), 256, sm, G.stream>>>(ma)
+            GB_FOR_SEMIRING(xt, zt, add, mul, K_MSMALL, err); GB_LAUNCHED();
+        }
+        if (n_medium) {
+            ma.chunk_row = m_row; ma.chunk_idx = m_idx; ma.chunk_cnt = m_cnt; ma.nchunks = n_medium; g.table = MEDIUM_TABLE;
+            const size_t sm = masked_smem(MEDIUM_TABLE, 1, wsize);
 #define K_MMEDIUM(XT, ZT, A_, M_) do { \
-                cudaFuncSetAttribute(masked_hash_kernel<XT, ZT, A_, M_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-                masked_hash_kernel<XT, ZT, A_, M_, false><<<(unsigned)g.nbin, 256, sm, G.stream>>>(g); } while (0)
-                GB_FOR_SEMIRING(xt, zt, add, mul, K_MMEDIUM, err); GB_LAUNCHED();
-            }
-            if (bins.count[3]) {
-                g.rows = bins.rows + bins.offset[3]; g.nbin = bins.count[3];
-                const int ctas = std::max(1, std::min<int>((int)bins.count[3], G.num_sms * 2));
-                GB_TRY(dalloc(&g.spa_slot, (size_t)ctas * ncols, err));
-                CU_TRY(cudaMemsetAsync(g.spa_slot, 0xFF, (size_t)ctas * ncols * 4, G.stream), err);
-                GB_TRY(dalloc(&g.queue, 1, err));
-                CU_TRY(cudaMemsetAsync(g.queue, 0, 4, G.stream), err);
-                void *words = tval;            // accumulate in 32/64-bit words; narrow types convert afterwards
-                if (zsz < 4) GB_TRY(dmalloc(&words, (size_t)M.nnz * 4 + 16, err));
-                g.spa_val = words;
-#define K_MSPA(XT, ZT, A_, M_) masked_spa_kernel<XT, ZT, A_, M_><<<ctas, 512, 0, G.stream>>>(g)
-                GB_FOR_SEMIRING(xt, zt, add, mul, K_MSPA, err); GB_LAUNCHED();
-                if (zsz < 4) {
-                    unpack_rows_kernel<<<grid_for(g.nbin * 32), 256, 0, G.stream>>>(g.rows, g.nbin, M.rowptr32, (const uint32_t *)words,
-                                                                                     (uint8_t *)tval, (int)zsz); GB_LAUNCHED();
-                    dfree(words);
-                }
-                dfree(g.spa_slot); dfree(g.queue);
-            }
-            dfree(bins.rows);
+            cudaFuncSetAttribute(masked_hash_kernel<XT, ZT, A_, M_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+            masked_hash_kernel<XT, ZT, A_, M_, false><<<(unsigned)n_medium, 256, sm, G.stream>>>(ma); } while (0)
+            GB_FOR_SEMIRING(xt, zt, add, mul, K_MMEDIUM, err); GB_LAUNCHED();
+        }
+        if (n_long) {
+            ma.chunk_row = l_row; ma.chunk_idx = l_idx; ma.chunk_cnt = l_cnt; ma.nchunks = n_long;
+            const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>(n_long, (int64_t)G.num_sms * 2));
+            GB_TRY(dalloc(&g.spa_slot, (size_t)ctas * ncols, err));
+            CU_TRY(cudaMemsetAsync(g.spa_slot, 0xFF, (size_t)ctas * ncols * 4, G.stream), err);
+            GB_TRY(dalloc(&g.queue, 1, err));
+            CU_TRY(cudaMemsetAsync(g.queue, 0, 4, G.stream), err);
+#define K_MSPA(XT, ZT, A_, M_) masked_spa_kernel<XT, ZT, A_, M_><<<ctas, 512, 0, G.stream>>>(ma)
+            GB_FOR_SEMIRING(xt, zt, add, mul, K_MSPA, err); GB_LAUNCHED();
+            dfree(g.spa_slot); dfree(g.queue);
+        }
+        dfree(m_row); dfree(m_idx); dfree(m_cnt); dfree(l_row); dfree(l_idx); dfree(l_cnt); dfree(w_rows);
+        if (zsz < 4) {      // narrow 32-bit accumulator words to the 1- or 2-byte type, in a second buffer
+            void *typed = nullptr;
+            GB_TRY(dmalloc(&typed, (size_t)M.nnz * zsz + 16, err));
+            narrow_words_kernel<<<grid_for(M.nnz), 256, 0, G.stream>>>((const uint32_t *)words, (uint8_t *)typed, (int)zsz, M.nnz); GB_LAUNCHED();
+            dfree(words); words = typed;
         }
     }
+    void *tval = words;
     // compact (pattern of M, found) -> CSR
     GB_TRY(dalloc(&T.rowptr, (size_t)nrows + 1, err));
     CU_TRY(cudaMemsetAsync(T.rowptr, 0, ((size_t)nrows + 1) * 8, G.stream), err);

@@ -177,14 +177,20 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_tile_kernel(const SpmvArgs 
     };
     for (int64_t r = r0 + threadIdx.x; r <= r1; r += SPMV_THREADS) {
         const int64_t rs = p.rowptr[r], re = p.rowptr[r + 1];
-        if (rs == re) { p.tpres[r] = 0; tval[r] = (ZT)0; continue; }                    // empty row: no entry
+        if (rs == re) { p.tpres[r] = 0; tval[r] = (ZT)0; continue; }   // empty row: no entry
         if (rs >= tend && !last) continue;                             // starts in the next tile
         const int s = (int)(max(rs, tstart) - tstart), e = (int)(min(re, tend) - tstart);
         if (e - s > SPMV_LONG) { s_queue[atomicAdd(&s_qcount, 1)] = (int)(r - r0); continue; }
-        ZT acc = ident; uint8_t has = sparse_u ? 0 : 1;
-        for (int k = s; k < e; ++k) {
-            acc = MulApply<ZT, ZT>::f(add, acc, s_prod[pad_idx(k)]);
-            if (sparse_u) has |= s_has[pad_idx(k)];
+        ZT acc; uint8_t has;
+        if (!sparse_u) {                       // every entry contributes: fold left to right
+            acc = s_prod[pad_idx(s)]; has = 1;
+            for (int k = s + 1; k < e; ++k) acc = MulApply<ZT, ZT>::f(add, acc, s_prod[pad_idx(k)]);
+        } else {                               // only entries whose u(k) is present contribute
+            acc = ident; has = 0;
+            for (int k = s; k < e; ++k) if (s_has[pad_idx(k)]) {
+                const ZT v = s_prod[pad_idx(k)];
+                acc = has ? MulApply<ZT, ZT>::f(add, acc, v) : v; has = 1;
+            }
         }
         emit(r, rs, re, acc, has);
     }
@@ -195,15 +201,16 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_tile_kernel(const SpmvArgs 
         const int64_t r = r0 + s_queue[q];
         const int64_t rs = p.rowptr[r], re = p.rowptr[r + 1];
         const int s = (int)(max(rs, tstart) - tstart), e = (int)(min(re, tend) - tstart);
-        ZT acc = ident; int has = sparse_u ? 0 : 1;
-        for (int k = s + lane; k < e; k += 32) {
-            acc = MulApply<ZT, ZT>::f(add, acc, s_prod[pad_idx(k)]);
-            if (sparse_u) has |= s_has[pad_idx(k)];
+        ZT acc = ident; int has = 0;
+        for (int k = s + lane; k < e; k += 32) if (!sparse_u || s_has[pad_idx(k)]) {
+            const ZT v = s_prod[pad_idx(k)];
+            acc = has ? MulApply<ZT, ZT>::f(add, acc, v) : v; has = 1;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            acc = MulApply<ZT, ZT>::f(add, acc, shfl_xor_t<ZT>(acc, o));
-            has |= __shfl_xor_sync(0xffffffffu, has, o);
+            const ZT ov = shfl_xor_t<ZT>(acc, o);
+            const int oh = __shfl_xor_sync(0xffffffffu, has, o);
+            if (oh) { acc = has ? MulApply<ZT, ZT>::f(add, acc, ov) : ov; has = 1; }
         }
         if (lane == 0) emit(r, rs, re, acc, (uint8_t)has);
     }
@@ -223,15 +230,16 @@ __global__ void __launch_bounds__(256) spmv_fixup_kernel(const SpmvArgs p) {
     const int64_t re = p.rowptr[r + 1];
     const int64_t last_tile = (re - 1) / SPMV_TILE;
     ZT acc = ident; int has = 0;
-    if (lane == 0) { acc = static_cast<const ZT *>(p.tail_val)[t]; has = p.tail_has[t]; }
-    for (int64_t tt = t + 1 + lane; tt <= last_tile; tt += 32) {
-        acc = MulApply<ZT, ZT>::f(add, acc, static_cast<const ZT *>(p.head_val)[tt]);
-        has |= p.head_has[tt];
+    if (lane == 0 && p.tail_has[t]) { acc = static_cast<const ZT *>(p.tail_val)[t]; has = 1; }
+    for (int64_t tt = t + 1 + lane; tt <= last_tile; tt += 32) if (p.head_has[tt]) {
+        const ZT v = static_cast<const ZT *>(p.head_val)[tt];
+        acc = has ? MulApply<ZT, ZT>::f(add, acc, v) : v; has = 1;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        acc = MulApply<ZT, ZT>::f(add, acc, shfl_xor_t<ZT>(acc, o));
-        has |= __shfl_xor_sync(0xffffffffu, has, o);
+        const ZT ov = shfl_xor_t<ZT>(acc, o);
+        const int oh = __shfl_xor_sync(0xffffffffu, has, o);
+        if (oh) { acc = has ? MulApply<ZT, ZT>::f(add, acc, ov) : ov; has = 1; }
     }
     if (lane == 0) { static_cast<ZT *>(p.tval)[r] = acc; p.tpres[r] = (uint8_t)(has != 0); }
 }
