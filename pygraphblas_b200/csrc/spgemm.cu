@@ -407,6 +407,47 @@ __device__ __forceinline__ void stream_b_rows(const GemmArgs &p, uint32_t pa0, u
     }
 }
 
+// Load-balanced streaming of the B rows named by A entries [c0, c1) for a whole CTA of NT threads:
+// NT entries at a time, the B-row lengths are prefix-summed in shared memory and the flattened
+// (entry, position) space is dealt out in runs of 4 consecutive positions per thread, so a hub B row
+// is spread over the whole CTA and short rows do not leave lanes idle.
+template <int NT, typename XT, typename Hit>
+__device__ __forceinline__ void flat_stream(const GemmArgs &p, uint32_t c0, uint32_t c1, uint32_t *s_off, uint32_t *s_bs, XT *s_av,
+                                            int *s_warp, Hit &&hit) {
+    const XT *aval = static_cast<const XT *>(p.a_val);
+    const int tid = threadIdx.x;
+    for (uint32_t base = c0; base < c1; base += NT) {
+        const uint32_t pa = base + tid;
+        const bool valid = pa < c1;
+        uint32_t bs = 0, len = 0;
+        XT av = (XT)1;
+        if (valid) {
+            const uint32_t k = __ldg(p.a_col + pa);
+            bs = __ldg(p.b_ptr + k); len = __ldg(p.b_ptr + k + 1) - bs;
+            if (p.need_a) av = gload<XT>(aval + pa);
+        }
+        int total = 0;
+        const int off = block_exclusive_scan((int)len, s_warp, &total);
+        s_off[tid] = (uint32_t)off; s_bs[tid] = bs; s_av[tid] = av;
+        __syncthreads();
+        const int nent = (int)min((uint32_t)NT, c1 - base);
+        for (uint32_t f0 = (uint32_t)tid * 4u; f0 < (uint32_t)total; f0 += NT * 4u) {
+            int lo = 0, hi = nent - 1;                       // largest e with s_off[e] <= f0
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= f0) lo = mid; else hi = mid - 1; }
+            int e = lo;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t f = f0 + i;
+                if (f >= (uint32_t)total) break;
+                while (e + 1 < nent && s_off[e + 1] <= f) ++e;
+                const uint32_t pb = s_bs[e] + (f - s_off[e]);
+                hit(__ldg(p.b_col + pb), s_av[e], pb);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <typename XT, typename ZT, int ADD, int MUL, bool WARP>
 __global__ void __launch_bounds__(256) masked_hash_kernel(const MaskedArgs ma) {
     typedef typename SlotWord<ZT>::W W;
@@ -475,16 +516,13 @@ __global__ void __launch_bounds__(256) masked_hash_kernel(const MaskedArgs ma) {
         const uint32_t as = p.a_ptr[row], ae = p.a_ptr[row + 1];
         if (WARP) stream_b_rows<XT, ZT>(p, as, ae, lane, hit);
         else {
-            // this chunk's slice of A(i,:), handed to the warps 32 entries at a time
+            // this chunk's slice of A(i,:): flattened over the whole CTA
+            __shared__ uint32_t s_off[256], s_bs[256];
+            __shared__ XT s_av[256];
+            __shared__ int s_warp[33];
             const uint32_t alen = ae - as;
             const uint32_t c0 = as + (uint32_t)(((uint64_t)alen * part) / nparts), c1 = as + (uint32_t)(((uint64_t)alen * (part + 1)) / nparts);
-            while (true) {
-                uint32_t b = 0;
-                if (lane == 0) b = atomicAdd(&s_next, 32u);
-                b = __shfl_sync(0xffffffffu, b, 0);
-                if (c0 + b >= c1) break;
-                stream_b_rows<XT, ZT>(p, c0 + b, min(c0 + b + 32u, c1), lane, hit);
-            }
+            flat_stream<256, XT>(p, c0, c1, s_off, s_bs, s_av, s_warp, hit);
         }
     }
     group_sync<WARP>();
@@ -507,7 +545,10 @@ template <typename XT, typename ZT, int ADD, int MUL>
 __global__ void __launch_bounds__(512) masked_spa_kernel(const MaskedArgs ma) {
     typedef typename SlotWord<ZT>::W W;
     const GemmArgs &p = ma.g;
-    __shared__ unsigned int s_next, s_sub;
+    __shared__ unsigned int s_next;
+    __shared__ uint32_t s_off[512], s_bs[512];
+    __shared__ XT s_av[512];
+    __shared__ int s_warp[33];
     const int add = ADD >= 0 ? ADD : p.add_op;
     const int mul = MUL >= 0 ? MUL : p.mul_op;
     int32_t *slot = p.spa_slot + (size_t)blockIdx.x * p.ncols;      // -1 everywhere when idle
@@ -515,7 +556,7 @@ __global__ void __launch_bounds__(512) masked_spa_kernel(const MaskedArgs ma) {
     W *tw = static_cast<W *>(ma.t_words);
     const int lane = threadIdx.x & 31;
     while (true) {
-        if (threadIdx.x == 0) { s_next = atomicAdd(p.queue, 1u); s_sub = 0; }
+        if (threadIdx.x == 0) s_next = atomicAdd(p.queue, 1u);
         __syncthreads();
         const unsigned int idx = s_next;
         if (idx >= ma.nchunks) break;
@@ -538,13 +579,7 @@ __global__ void __launch_bounds__(512) masked_spa_kernel(const MaskedArgs ma) {
         };
         const uint32_t as = p.a_ptr[row], ae = p.a_ptr[row + 1], alen = ae - as;
         const uint32_t c0 = as + (uint32_t)(((uint64_t)alen * part) / nparts), c1 = as + (uint32_t)(((uint64_t)alen * (part + 1)) / nparts);
-        while (true) {
-            uint32_t b = 0;
-            if (lane == 0) b = atomicAdd(&s_sub, 32u);
-            b = __shfl_sync(0xffffffffu, b, 0);
-            if (c0 + b >= c1) break;
-            stream_b_rows<XT, ZT>(p, c0 + b, min(c0 + b + 32u, c1), lane, hit);
-        }
+        flat_stream<512, XT>(p, c0, c1, s_off, s_bs, s_av, s_warp, hit);
         __syncthreads();
         for (uint32_t q = ms + threadIdx.x; q < me; q += blockDim.x) slot[p.m_col[q]] = -1;
         __syncthreads();
@@ -1064,10 +1099,12 @@ extern "C" GrB_Info GrB_mxm(GrB_Matrix C, const GrB_Matrix Mask, const GrB_Binar
 
     // masked methods apply to non-complemented masks
     const bool use_mask = Mask && !f.mask_comp;
-    const bool dot = use_mask && f.tran1;           // C<M> = A*B': intersect rows of A and B, no transpose
-
     if (f.tran0) GB_TRY(matrix_ensure_transpose(A)); else GB_TRY(matrix_ensure_device(A));
-    if (f.tran1 && !dot) GB_TRY(matrix_ensure_transpose(B)); else GB_TRY(matrix_ensure_device(B));
+    GB_TRY(matrix_ensure_device(B));
+    // C<M> = A*B': small problems intersect rows of A and B directly (no transpose); large ones
+    // go through the cached transpose and the load-balanced masked hash kernels
+    const bool dot = use_mask && f.tran1 && B->dev.nnz < ((int64_t)1 << 18);
+    if (f.tran1 && !dot) GB_TRY(matrix_ensure_transpose(B));
     if (Mask) GB_TRY(matrix_ensure_device(Mask));
     const Csr &a = f.tran0 ? A->devT : A->dev;
     const Csr &b = (f.tran1 && !dot) ? B->devT : B->dev;

@@ -228,6 +228,52 @@ def test_rmat_triangle_count_masked_mxm():
     assert C3.iseq(C)
 
 
+def test_rmat_masked_mxm_large_ST1_and_valued_mask():
+    """Above 2^18 entries C<M> = A*B' runs through the cached transpose + chunked masked hash kernels."""
+    n, indptr, indices = _rmat(15)
+    S = sp.csr_matrix((np.ones(len(indices)), indices, indptr), shape=(n, n))
+    Ls = sp.tril(S + S.T, -1).tocsr(); Ls.sort_indices(); Ls.data[:] = 1
+    assert Ls.nnz >= 1 << 18
+    rng = np.random.default_rng(9)
+    lv = rng.integers(1, 4, Ls.nnz).astype(np.int64)
+    L = Matrix.from_csr(Ls.indptr, Ls.indices, lv, n, n, INT64)
+    Lw = sp.csr_matrix((lv.astype(np.float64), Ls.indices, Ls.indptr), shape=(n, n))
+    C = L.mxm(L, mask=L, semiring=INT64.PLUS_TIMES, desc=descriptor.ST1)
+    R = (Lw @ Lw.T).multiply(Ls).tocsr(); R.sort_indices(); R.eliminate_zeros()
+    Ap, Aj, Ax = C.to_csr()
+    assert np.array_equal(Ap, R.indptr) and np.array_equal(Aj, R.indices) and np.array_equal(Ax, R.data.astype(np.int64))
+    # valued mask: entries with value 0 mask nothing in
+    mv = (rng.integers(0, 2, Ls.nnz)).astype(np.int64)
+    Mk = Matrix.from_csr(Ls.indptr, Ls.indices, mv, n, n, INT64)
+    C2 = L.mxm(L, mask=Mk, semiring=INT64.PLUS_TIMES)
+    Mp = sp.csr_matrix((mv.astype(np.float64), Ls.indices, Ls.indptr), shape=(n, n)); Mp.eliminate_zeros()
+    R2 = (Lw @ Lw).multiply(Mp > 0).tocsr(); R2.sort_indices(); R2.eliminate_zeros()
+    Bp, Bj, Bx = C2.to_csr()
+    assert np.array_equal(Bp, R2.indptr) and np.array_equal(Bj, R2.indices) and np.array_equal(Bx, R2.data.astype(np.int64))
+
+
+def test_hot_column_spmv_matches_plain_kernel():
+    """Large dense-u SpMV takes the relabelled hot-column kernel; results must be bit-identical to the
+    plain tile kernel (same per-row product order), for specialised and run-time semirings."""
+    import os
+    n, indptr, indices = _rmat(17)
+    assert len(indices) >= 1 << 20
+    rng = np.random.default_rng(11)
+    for typ, sr_names in ((FP32, ["PLUS_TIMES", "MIN_PLUS", "MAX_MIN"]), (INT64, ["PLUS_TIMES", "MIN_FIRST"]), (FP64, ["PLUS_SECOND"])):
+        vals = rng.integers(1, 9, len(indices)).astype(typ.dtype)
+        u = rng.integers(0, 9, n).astype(typ.dtype)
+        A = Matrix.from_csr(indptr, indices, vals, n, n, typ)
+        rows = np.repeat(np.arange(n), np.diff(indptr))
+        for name in sr_names:
+            w = A.mxv(Vector.from_numpy(u), semiring=getattr(typ, name))
+            x, p = w.to_numpy()
+            add, mul = name.split("_")
+            ref = orc.mxv(orc.SpVec(typ.name, n), None, None, (add, mul, typ.name), orc.SpMat(typ.name, n, n, rows, indices, vals),
+                          orc.SpVec(typ.name, n, np.arange(n), u))
+            assert np.array_equal(np.nonzero(p)[0], ref.I), name
+            assert np.array_equal(x[p != 0], ref.X), name      # small integers: exact in every type
+
+
 def test_rmat_unmasked_spgemm_matches_scipy():
     """configs[3] secondary: unmasked A (+.second) A, all three row bins (hash / hash / dense accumulator)."""
     n, indptr, indices = _rmat(12)
