@@ -248,12 +248,11 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_tile_kernel(const SpmvArgs 
 // the hot_n most frequently referenced columns (the matrix's columns were relabelled by descending
 // in-degree, so "hot" is simply "id < hot_n").  On R-MAT graphs ~55-60% of all gathers hit the table,
 // which takes them off the L1TEX wavefront path that otherwise bounds the kernel.
-static constexpr int HOT_GROUPS = 4;
 template <typename ZT> __host__ __device__ constexpr size_t hot_group_bytes() {
     return ((SPMV_PROD_WORDS * sizeof(ZT) + (SPMV_QUEUE + 1) * sizeof(int)) + 15) & ~(size_t)15;
 }
-template <typename XT, typename ZT, int ADD, int MUL>
-__global__ void __launch_bounds__(SPMV_THREADS * HOT_GROUPS, 1) spmv_hot_kernel(const SpmvArgs p, const uint32_t hot_n) {
+template <typename XT, typename ZT, int ADD, int MUL, int HOT_GROUPS>
+__global__ void __launch_bounds__(SPMV_THREADS * HOT_GROUPS) spmv_hot_kernel(const SpmvArgs p, const uint32_t hot_n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int group = threadIdx.x / SPMV_THREADS, gtid = threadIdx.x % SPMV_THREADS;
     unsigned char *gbase = smem_raw + (size_t)group * hot_group_bytes<ZT>();
@@ -317,24 +316,31 @@ __global__ void clear_presence_kernel(uint8_t *p, int64_t n) {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) p[k] = 0;
 }
 
-struct HotLaunch { bool on; int64_t hused; };
+struct HotLaunch { bool on; int64_t hused; int groups; size_t table_bytes; };
+
+template <typename XT, typename ZT, int ADD, int MUL, int GROUPS>
+static void spmv_hot_launch(const SpmvArgs &a, const HotLaunch &h) {
+    auto kernel = spmv_hot_kernel<XT, ZT, ADD, MUL, GROUPS>;
+    int max_optin = 0;
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, G.device);
+    const size_t fixed = GROUPS * hot_group_bytes<ZT>();
+    size_t avail = (size_t)max_optin > fixed + 1024 ? (size_t)max_optin - fixed - 1024 : 0;
+    avail = std::min(avail, h.table_bytes);
+    const uint32_t hot_n = (uint32_t)std::min<int64_t>(h.hused, (int64_t)(avail / sizeof(XT)));
+    const size_t smem = fixed + (size_t)hot_n * sizeof(XT);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SPMV_THREADS * GROUPS, smem);
+    per_sm = std::max(per_sm, 1);
+    const int ctas = (int)std::min<int64_t>((int64_t)G.num_sms * per_sm, ceil_div(a.ntiles, GROUPS));
+    kernel<<<ctas, SPMV_THREADS * GROUPS, smem, G.stream>>>(a, hot_n); GB_LAUNCHED();
+}
 
 template <typename XT, typename ZT, int ADD, int MUL>
 static void spmv_launch(const SpmvArgs &a, const HotLaunch &h) {
     bool launched = false;
     if constexpr (std::is_same<XT, ZT>::value) {
-        if (h.on) {
-            int max_optin = 0;
-            cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, G.device);
-            const size_t fixed = HOT_GROUPS * hot_group_bytes<ZT>();
-            const size_t avail = (size_t)max_optin > fixed + 1024 ? (size_t)max_optin - fixed - 1024 : 0;
-            const uint32_t hot_n = (uint32_t)std::min<int64_t>(h.hused, (int64_t)(avail / sizeof(XT)));
-            const size_t smem = fixed + (size_t)hot_n * sizeof(XT);
-            cudaFuncSetAttribute(spmv_hot_kernel<XT, ZT, ADD, MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            const int ctas = (int)std::min<int64_t>(G.num_sms, ceil_div(a.ntiles, HOT_GROUPS));
-            spmv_hot_kernel<XT, ZT, ADD, MUL><<<ctas, SPMV_THREADS * HOT_GROUPS, smem, G.stream>>>(a, hot_n); GB_LAUNCHED();
-            launched = true;
-        }
+        if (h.on) { launched = true; if (h.groups == 2) spmv_hot_launch<XT, ZT, ADD, MUL, 2>(a, h); else spmv_hot_launch<XT, ZT, ADD, MUL, 4>(a, h); }
     }
     if (!launched) { spmv_tile_kernel<XT, ZT, ADD, MUL><<<(unsigned)a.ntiles, SPMV_THREADS, 0, G.stream>>>(a); GB_LAUNCHED(); }
     spmv_fixup_kernel<ZT, ADD><<<(unsigned)ceil_div(a.ntiles * 32, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED();
@@ -533,9 +539,11 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
         GB_TRY(dmalloc((void **)&a.tail_has, (size_t)c.ntiles + 16, err));
         GB_TRY(dalloc(&a.tail_row, (size_t)c.ntiles, err));
         // dense u on a large matrix: hot-column plan + shared-memory table (see spmv_hot_kernel)
-        HotLaunch hot{false, 0};
+        HotLaunch hot{false, 0, 4, (size_t)64 << 10};
+        if (const char *e = getenv("B200GRB_HOT_GROUPS")) hot.groups = atoi(e);
+        if (const char *e = getenv("B200GRB_HOT_KB")) hot.table_bytes = (size_t)atoi(e) << 10;
         void *u_perm = nullptr;
-        static const bool no_hot = getenv("B200GRB_NO_HOT") != nullptr;
+        const bool no_hot = getenv("B200GRB_NO_HOT") != nullptr;
         if (!no_hot && need_u && !u->dpres && xt == zt && c.nnz >= ((int64_t)1 << 20) && c.ncols >= (1 << 16)) {
             GB_TRY(spmv_hot_plan(c, err));
             const size_t xsz = (size_t)tc_size(xt);

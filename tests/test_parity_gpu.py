@@ -246,7 +246,7 @@ def test_rmat_masked_mxm_large_ST1_and_valued_mask():
     mv = (rng.integers(0, 2, Ls.nnz)).astype(np.int64)
     Mk = Matrix.from_csr(Ls.indptr, Ls.indices, mv, n, n, INT64)
     C2 = L.mxm(L, mask=Mk, semiring=INT64.PLUS_TIMES)
-    Mp = sp.csr_matrix((mv.astype(np.float64), Ls.indices, Ls.indptr), shape=(n, n)); Mp.eliminate_zeros()
+    Mp = sp.csr_matrix((mv.astype(np.float64), Ls.indices.copy(), Ls.indptr.copy()), shape=(n, n)); Mp.eliminate_zeros()
     R2 = (Lw @ Lw).multiply(Mp > 0).tocsr(); R2.sort_indices(); R2.eliminate_zeros()
     Bp, Bj, Bx = C2.to_csr()
     assert np.array_equal(Bp, R2.indptr) and np.array_equal(Bj, R2.indices) and np.array_equal(Bx, R2.data.astype(np.int64))
