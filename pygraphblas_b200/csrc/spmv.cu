@@ -144,55 +144,65 @@ __device__ __forceinline__ void spmv_tile_body(const SpmvArgs &p, const int64_t 
 
     if (gtid == 0) { *sm.qcount = 0; p.tail_row[tile] = -1; p.head_has[tile] = 0; p.tail_has[tile] = 0; }
 
-    // ---- stream the tile: 128-bit column / value loads, gather u, products to shared memory
+    // ---- stream the tile: 128-bit column / value loads, gather u, products to shared memory.
+    // All loads of a phase are issued back to back (no per-item control flow) so that every thread
+    // keeps 4 vector loads and then 8 gathers in flight: the kernel lives on memory-level parallelism.
+    constexpr int NI = SPMV_GROUPS * SPMV_VEC;
+    uint32_t c[NI]; XT a[NI]; bool ok[NI];
 #pragma unroll
     for (int g = 0; g < SPMV_GROUPS; ++g) {
-        const int loc = g * SPMV_THREADS * SPMV_VEC + gtid * SPMV_VEC;
-        const int64_t k0 = tstart + loc;
-        uint32_t c[4]; XT a[4]; bool ok[4];
+        const int64_t k0 = tstart + g * SPMV_THREADS * SPMV_VEC + gtid * SPMV_VEC;
         if (k0 + 3 < tend) {
-            load4<uint32_t>(p.col + k0, c);
-            if (p.need_a) load4<XT>(aval + k0, a);
-            ok[0] = ok[1] = ok[2] = ok[3] = true;
+            load4<uint32_t>(p.col + k0, *reinterpret_cast<uint32_t(*)[4]>(&c[g * 4]));
+            if (p.need_a) load4<XT>(aval + k0, *reinterpret_cast<XT(*)[4]>(&a[g * 4]));
+            ok[g * 4] = ok[g * 4 + 1] = ok[g * 4 + 2] = ok[g * 4 + 3] = true;
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                ok[j] = k0 + j < tend;
-                c[j] = ok[j] ? p.col[k0 + j] : 0u;
-                if (p.need_a && ok[j]) a[j] = aval[k0 + j];
+                ok[g * 4 + j] = k0 + j < tend;
+                c[g * 4 + j] = ok[g * 4 + j] ? p.col[k0 + j] : 0u;          // 0 is always a valid column to gather
+                if (p.need_a) a[g * 4 + j] = ok[g * 4 + j] ? aval[k0 + j] : (XT)1;
             }
         }
+    }
+    // row pointers of this thread's first row of the reduce phase: issued now, consumed after the barrier
+    const int64_t r0 = p.tile_row[tile];
+    const int64_t r1 = min((int64_t)p.tile_row[tile + 1], p.nrows - 1);
+    int64_t pre_rs = 0, pre_re = 0;
+    if (r0 + gtid <= r1) { pre_rs = p.rowptr[r0 + gtid]; pre_re = p.rowptr[r0 + gtid + 1]; }
+    uint8_t hs[NI]; XT uv[NI];
+    if (sparse_u) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            ZT z = ident; uint8_t has = 0;
-            if (ok[j]) {
-                has = sparse_u ? __ldg(p.upres + c[j]) : (uint8_t)1;
-                if (has) {
-                    const XT av = p.need_a ? a[j] : (XT)1;
-                    XT uv = (XT)1;
-                    if (p.need_u) {
-                        if (HOT && c[j] < hot_n) uv = s_hot[c[j]];
-                        else uv = gload<XT>(uval + c[j]);
-                    }
-                    z = p.flip ? MulApply<XT, ZT>::f(mul, uv, av) : MulApply<XT, ZT>::f(mul, av, uv);
-                }
-            }
-            s_prod[pad_idx(loc + j)] = z;
-            if (sparse_u) s_has[pad_idx(loc + j)] = has;
+        for (int j = 0; j < NI; ++j) hs[j] = __ldg(p.upres + c[j]);
+    }
+    if (p.need_u) {
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            if (HOT && c[j] < hot_n) uv[j] = s_hot[c[j]];
+            else uv[j] = gload<XT>(uval + c[j]);
         }
+    }
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+        const int loc = (j >> 2) * SPMV_THREADS * SPMV_VEC + gtid * SPMV_VEC + (j & 3);
+        const bool has = ok[j] && (!sparse_u || hs[j]);
+        const XT av = p.need_a ? a[j] : (XT)1;
+        const XT uu = p.need_u ? uv[j] : (XT)1;
+        const ZT z = p.flip ? MulApply<XT, ZT>::f(mul, uu, av) : MulApply<XT, ZT>::f(mul, av, uu);
+        s_prod[pad_idx(loc)] = has ? z : ident;
+        if (sparse_u) s_has[pad_idx(loc)] = (uint8_t)has;
     }
     group_barrier(bar_id, SPMV_THREADS);
 
     // ---- reduce the row segments inside the tile
-    const int64_t r0 = p.tile_row[tile];
-    const int64_t r1 = min((int64_t)p.tile_row[tile + 1], p.nrows - 1);
     auto emit = [&](int64_t r, int64_t rs, int64_t re, ZT acc, uint8_t has) {
         if (rs >= tstart && re <= tend) { tval[r] = acc; p.tpres[r] = has; }
         else if (rs < tstart) { static_cast<ZT *>(p.head_val)[tile] = acc; p.head_has[tile] = has; }
         else { static_cast<ZT *>(p.tail_val)[tile] = acc; p.tail_has[tile] = has; p.tail_row[tile] = (int32_t)r; }
     };
     for (int64_t r = r0 + gtid; r <= r1; r += SPMV_THREADS) {
-        const int64_t rs = p.rowptr[r], re = p.rowptr[r + 1];
+        const bool first = r == r0 + gtid;
+        const int64_t rs = first ? pre_rs : (int64_t)p.rowptr[r], re = first ? pre_re : (int64_t)p.rowptr[r + 1];
         if (rs == re) { p.tpres[r] = 0; tval[r] = (ZT)0; continue; }   // empty row: no entry
         if (rs >= tend && !last) continue;                             // starts in the next tile
         const int s = (int)(max(rs, tstart) - tstart), e = (int)(min(re, tend) - tstart);
@@ -234,7 +244,7 @@ __device__ __forceinline__ void spmv_tile_body(const SpmvArgs &p, const int64_t 
 
 // One CTA per tile (general path: any u, any semiring).
 template <typename XT, typename ZT, int ADD, int MUL>
-__global__ void __launch_bounds__(SPMV_THREADS) spmv_tile_kernel(const SpmvArgs p) {
+__global__ void __launch_bounds__(SPMV_THREADS, 5) spmv_tile_kernel(const SpmvArgs p) {
     __shared__ ZT s_prod[SPMV_PROD_WORDS];
     __shared__ uint8_t s_has[SPMV_PROD_WORDS];
     __shared__ int s_queue[SPMV_QUEUE];

@@ -24,8 +24,11 @@ class Descriptor:
         return self._desc[0]
 
     def __del__(self):
-        if getattr(self, "_owned", False) and lib is not None:
-            lib.GrB_Descriptor_free(self._desc)
+        try:
+            if getattr(self, "_owned", False) and lib is not None:
+                lib.GrB_Descriptor_free(self._desc)
+        except Exception:
+            pass
 
     def __getitem__(self, field):
         val = ffi.new("GrB_Desc_Value*")

@@ -28,8 +28,11 @@ class Matrix:
         self._keep = None
 
     def __del__(self):
-        if lib is not None and getattr(self, "_matrix", None) is not None:
-            lib.GrB_Matrix_free(self._matrix)
+        try:        # at interpreter shutdown the binding may already be torn down
+            if lib is not None and getattr(self, "_matrix", None) is not None:
+                lib.GrB_Matrix_free(self._matrix)
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ construction
     @classmethod

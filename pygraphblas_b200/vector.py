@@ -20,8 +20,11 @@ class Vector:
         self._vector = handle
 
     def __del__(self):
-        if lib is not None and getattr(self, "_vector", None) is not None:
-            lib.GrB_Vector_free(self._vector)
+        try:        # at interpreter shutdown the binding may already be torn down
+            if lib is not None and getattr(self, "_vector", None) is not None:
+                lib.GrB_Vector_free(self._vector)
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ construction
     @classmethod
