@@ -18,7 +18,7 @@ sp_ = gb.ffi.new("void**"); gb.lib.B200_get_stream(sp_)
 stream = torch.cuda.ExternalStream(int(gb.ffi.cast("uintptr_t", sp_[0])))
 
 def run(label, env):
-    for k in ("B200GRB_NO_HOT", "B200GRB_HOT_GROUPS", "B200GRB_HOT_KB"):
+    for k in ("B200GRB_NO_HOT", "B200GRB_HOT_GROUPS", "B200GRB_HOT_KB", "B200GRB_RELABEL_ONLY"):
         os.environ.pop(k, None)
     os.environ.update(env)
     for _ in range(5):
@@ -34,6 +34,7 @@ def run(label, env):
     print(f"{label:32s} {ms*1e3:8.1f} us  {len(indices)/ms/1e6:7.1f} GEdge/s", flush=True)
 
 run("plain tile kernel", {"B200GRB_NO_HOT": "1"})
+run("plain kernel, relabelled columns", {"B200GRB_RELABEL_ONLY": "1"})
 for groups in (4, 2):
-    for kb in (8, 16, 32, 48, 64, 96, 128, 160, 192):
+    for kb in (16, 32, 64, 128, 160):
         run(f"hot groups={groups} table={kb}KB", {"B200GRB_HOT_GROUPS": str(groups), "B200GRB_HOT_KB": str(kb)})
