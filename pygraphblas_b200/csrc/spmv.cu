@@ -29,8 +29,6 @@ static constexpr int SPMV_THREADS = 256;
 static constexpr int SPMV_VEC = 4;                       // entries per 128-bit column load
 static constexpr int SPMV_GROUPS = 2;                    // 128-bit loads per thread per array
 static constexpr int SPMV_TILE = SPMV_THREADS * SPMV_VEC * SPMV_GROUPS;   // 2048 nnz per CTA
-static constexpr int SPMV_LONG = 64;                     // segments longer than this go warp-per-row
-static constexpr int SPMV_QUEUE = SPMV_TILE / SPMV_LONG + 1;
 
 struct SpmvArgs {
     const uint32_t *rowptr; const uint32_t *col; const void *aval;
@@ -122,14 +120,42 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-static constexpr int SPMV_PROD_WORDS = SPMV_TILE + SPMV_TILE / 32;
+// A partial monoid value: `has` says whether anything was folded in yet (identity-free, so that
+// ANY and user-visible "no entry" semantics need no special cases).
+template <typename ZT> struct Part { ZT v; int has; };
+template <typename ZT> __device__ __forceinline__ Part<ZT> part_join(int add, Part<ZT> a, Part<ZT> b) {
+    Part<ZT> r;
+    r.has = a.has | b.has;
+    r.v = a.has ? (b.has ? MulApply<ZT, ZT>::f(add, a.v, b.v) : a.v) : b.v;
+    return r;
+}
+template <typename T> __device__ __forceinline__ T shfl_down_t(T v, int d) {
+    if constexpr (sizeof(T) == 8) { long long x = reinterpret_cast<long long &>(v); x = __shfl_down_sync(0xffffffffu, x, d); return reinterpret_cast<T &>(x); }
+    else if constexpr (sizeof(T) == 4) { int x = reinterpret_cast<int &>(v); x = __shfl_down_sync(0xffffffffu, x, d); return reinterpret_cast<T &>(x); }
+    else { int x = (int)v; x = __shfl_down_sync(0xffffffffu, x, d); return (T)x; }
+}
 
 // Shared-memory working set of one 256-thread group processing one tile.
 template <typename ZT> struct TileSmem {
-    ZT *prod; uint8_t *has; int *queue; int *qcount;
+    int32_t *headrow;      // [SPMV_TILE] row (relative to the tile's first row) starting at this entry, or -1
+    ZT *wv; int *wflag;    // [8] per-warp scan aggregates: value, (has | stop << 1)
 };
+static constexpr int SPMV_WARPS = SPMV_THREADS / 32;
+static constexpr int SPMV_ITEMS = SPMV_VEC * SPMV_GROUPS;       // consecutive entries per thread
 
 // One tile of SPMV_TILE entries handled by a group of SPMV_THREADS threads (gtid = 0..255).
+//
+//   1. every thread streams its 8 consecutive entries (two 128-bit loads per array), gathers u and
+//      keeps the 8 products in registers;
+//   2. the rows of the tile are walked thread-per-row (coalesced rowptr reads): empty rows are
+//      written out as "no entry", the others mark their first entry in shared memory;
+//   3. item-centric segmented reduction: each thread folds its 8 items between row marks (rows
+//      that begin and end inside a thread are final), then a segmented suffix scan over the
+//      threads (shuffles inside a warp, 8 aggregates across warps) completes the rows that span
+//      threads.  Work per thread is constant, whatever the row lengths: hub rows and runs of
+//      short rows cost the same.
+//   4. what sticks out of the tile goes to the per-tile head / tail slots for the fix-up kernel.
+//
 // HOT: columns are the relabelled ids of the hot-column plan; ids below hot_n are read from the
 // shared-memory table s_hot instead of going through L1/L2.
 template <typename XT, typename ZT, int ADD, int MUL, bool HOT>
@@ -137,134 +163,142 @@ __device__ __forceinline__ void spmv_tile_body(const SpmvArgs &p, const int64_t 
                                                const uint32_t hot_n, const int gtid, const int bar_id) {
     const int add = ADD >= 0 ? ADD : p.add_op;
     const int mul = MUL >= 0 ? MUL : p.mul_op;
-    const ZT ident = monoid_identity<ZT>(add);
     const int64_t tstart = tile * SPMV_TILE;
     const int64_t tend = min(tstart + (int64_t)SPMV_TILE, p.nnz);
-    const bool last = tile == p.ntiles - 1;
     const bool sparse_u = !HOT && p.upres != nullptr;
     const XT *aval = static_cast<const XT *>(p.aval);
     const XT *uval = static_cast<const XT *>(p.uval);
     ZT *tval = static_cast<ZT *>(p.tval);
-    ZT *s_prod = sm.prod; uint8_t *s_has = sm.has; int *s_queue = sm.queue;
+    const int lane = gtid & 31, warp = gtid >> 5;
+    const int loc0 = gtid * SPMV_ITEMS;
+    const int64_t k0 = tstart + loc0;
 
-    if (gtid == 0) { *sm.qcount = 0; p.tail_row[tile] = -1; p.head_has[tile] = 0; p.tail_has[tile] = 0; }
-
-    // ---- stream the tile: 128-bit column / value loads, gather u, products to shared memory.
-    // All loads of a phase are issued back to back (no per-item control flow) so that every thread
-    // keeps 4 vector loads and then 8 gathers in flight: the kernel lives on memory-level parallelism.
-    constexpr int NI = SPMV_GROUPS * SPMV_VEC;
-    uint32_t c[NI]; XT a[NI]; bool ok[NI];
+    // ---- (1) stream: all loads of a phase are issued back to back (memory-level parallelism)
+    uint32_t c[SPMV_ITEMS]; XT a[SPMV_ITEMS]; bool ok[SPMV_ITEMS];
+    if (k0 + SPMV_ITEMS <= tend) {
 #pragma unroll
-    for (int g = 0; g < SPMV_GROUPS; ++g) {
-        const int64_t k0 = tstart + g * SPMV_THREADS * SPMV_VEC + gtid * SPMV_VEC;
-        if (k0 + 3 < tend) {
-            load4<uint32_t>(p.col + k0, *reinterpret_cast<uint32_t(*)[4]>(&c[g * 4]));
-            if (p.need_a) load4<XT>(aval + k0, *reinterpret_cast<XT(*)[4]>(&a[g * 4]));
-            ok[g * 4] = ok[g * 4 + 1] = ok[g * 4 + 2] = ok[g * 4 + 3] = true;
-        } else {
+        for (int g = 0; g < SPMV_GROUPS; ++g) {
+            load4<uint32_t>(p.col + k0 + g * 4, *reinterpret_cast<uint32_t(*)[4]>(&c[g * 4]));
+            if (p.need_a) load4<XT>(aval + k0 + g * 4, *reinterpret_cast<XT(*)[4]>(&a[g * 4]));
+        }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                ok[g * 4 + j] = k0 + j < tend;
-                c[g * 4 + j] = ok[g * 4 + j] ? p.col[k0 + j] : 0u;          // 0 is always a valid column to gather
-                if (p.need_a) a[g * 4 + j] = ok[g * 4 + j] ? aval[k0 + j] : (XT)1;
-            }
+        for (int j = 0; j < SPMV_ITEMS; ++j) ok[j] = true;
+    } else {
+#pragma unroll
+        for (int j = 0; j < SPMV_ITEMS; ++j) {
+            ok[j] = k0 + j < tend;
+            c[j] = ok[j] ? p.col[k0 + j] : 0u;                    // 0 is always a valid column to gather
+            if (p.need_a) a[j] = ok[j] ? aval[k0 + j] : (XT)1;
         }
     }
-    // row pointers of this thread's first row of the reduce phase: issued now, consumed after the barrier
     const int64_t r0 = p.tile_row[tile];
     const int64_t r1 = min((int64_t)p.tile_row[tile + 1], p.nrows - 1);
-    int64_t pre_rs = 0, pre_re = 0;
+    int64_t pre_rs = 0, pre_re = 0;                               // row pointers of this thread's first row
     if (r0 + gtid <= r1) { pre_rs = p.rowptr[r0 + gtid]; pre_re = p.rowptr[r0 + gtid + 1]; }
-    uint8_t hs[NI]; XT uv[NI];
+#pragma unroll
+    for (int j = 0; j < SPMV_ITEMS; j += 4) *reinterpret_cast<int4 *>(&sm.headrow[loc0 + j]) = make_int4(-1, -1, -1, -1);
+    if (gtid == 0) { p.tail_row[tile] = -1; p.head_has[tile] = 0; p.tail_has[tile] = 0; }
+    uint8_t hs[SPMV_ITEMS]; XT uv[SPMV_ITEMS];
     if (sparse_u) {
 #pragma unroll
-        for (int j = 0; j < NI; ++j) hs[j] = __ldg(p.upres + c[j]);
+        for (int j = 0; j < SPMV_ITEMS; ++j) hs[j] = __ldg(p.upres + c[j]);
     }
     if (p.need_u) {
 #pragma unroll
-        for (int j = 0; j < NI; ++j) {
+        for (int j = 0; j < SPMV_ITEMS; ++j) {
             if (HOT && c[j] < hot_n) uv[j] = s_hot[c[j]];
             else uv[j] = gload<XT>(uval + c[j]);
         }
     }
-#pragma unroll
-    for (int j = 0; j < NI; ++j) {
-        const int loc = (j >> 2) * SPMV_THREADS * SPMV_VEC + gtid * SPMV_VEC + (j & 3);
-        const bool has = ok[j] && (!sparse_u || hs[j]);
-        const XT av = p.need_a ? a[j] : (XT)1;
-        const XT uu = p.need_u ? uv[j] : (XT)1;
-        const ZT z = p.flip ? MulApply<XT, ZT>::f(mul, uu, av) : MulApply<XT, ZT>::f(mul, av, uu);
-        s_prod[pad_idx(loc)] = has ? z : ident;
-        if (sparse_u) s_has[pad_idx(loc)] = (uint8_t)has;
-    }
-    group_barrier(bar_id, SPMV_THREADS);
+    group_barrier(bar_id, SPMV_THREADS);                          // head marks are clear
 
-    // ---- reduce the row segments inside the tile
-    auto emit = [&](int64_t r, int64_t rs, int64_t re, ZT acc, uint8_t has) {
-        if (rs >= tstart && re <= tend) { tval[r] = acc; p.tpres[r] = has; }
-        else if (rs < tstart) { static_cast<ZT *>(p.head_val)[tile] = acc; p.head_has[tile] = has; }
-        else { static_cast<ZT *>(p.tail_val)[tile] = acc; p.tail_has[tile] = has; p.tail_row[tile] = (int32_t)r; }
-    };
+    // ---- (2) rows of the tile: empty ones are final, the others mark their first entry
     for (int64_t r = r0 + gtid; r <= r1; r += SPMV_THREADS) {
         const bool first = r == r0 + gtid;
         const int64_t rs = first ? pre_rs : (int64_t)p.rowptr[r], re = first ? pre_re : (int64_t)p.rowptr[r + 1];
-        if (rs == re) { p.tpres[r] = 0; tval[r] = (ZT)0; continue; }   // empty row: no entry
-        if (rs >= tend && !last) continue;                             // starts in the next tile
-        const int s = (int)(max(rs, tstart) - tstart), e = (int)(min(re, tend) - tstart);
-        if (e - s > SPMV_LONG) { s_queue[atomicAdd(sm.qcount, 1)] = (int)(r - r0); continue; }
-        ZT acc; uint8_t has;
-        if (!sparse_u) {                       // every entry contributes: fold left to right
-            acc = s_prod[pad_idx(s)]; has = 1;
-            for (int k = s + 1; k < e; ++k) acc = MulApply<ZT, ZT>::f(add, acc, s_prod[pad_idx(k)]);
-        } else {                               // only entries whose u(k) is present contribute
-            acc = ident; has = 0;
-            for (int k = s; k < e; ++k) if (s_has[pad_idx(k)]) {
-                const ZT v = s_prod[pad_idx(k)];
-                acc = has ? MulApply<ZT, ZT>::f(add, acc, v) : v; has = 1;
-            }
-        }
-        emit(r, rs, re, acc, has);
+        if (rs == re) { p.tpres[r] = 0; tval[r] = (ZT)0; }
+        else if (rs >= tstart && rs < tend) sm.headrow[rs - tstart] = (int32_t)(r - r0);
     }
-    group_barrier(bar_id, SPMV_THREADS);
-    const int nq = *sm.qcount;
-    const int lane = gtid & 31, warp = gtid >> 5;
-    for (int q = warp; q < nq; q += SPMV_THREADS / 32) {
-        const int64_t r = r0 + s_queue[q];
-        const int64_t rs = p.rowptr[r], re = p.rowptr[r + 1];
-        const int s = (int)(max(rs, tstart) - tstart), e = (int)(min(re, tend) - tstart);
-        ZT acc = ident; int has = 0;
-        for (int k = s + lane; k < e; k += 32) if (!sparse_u || s_has[pad_idx(k)]) {
-            const ZT v = s_prod[pad_idx(k)];
-            acc = has ? MulApply<ZT, ZT>::f(add, acc, v) : v; has = 1;
-        }
+    Part<ZT> prod[SPMV_ITEMS];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const ZT ov = shfl_xor_t<ZT>(acc, o);
-            const int oh = __shfl_xor_sync(0xffffffffu, has, o);
-            if (oh) { acc = has ? MulApply<ZT, ZT>::f(add, acc, ov) : ov; has = 1; }
+    for (int j = 0; j < SPMV_ITEMS; ++j) {
+        const XT av = p.need_a ? a[j] : (XT)1;
+        const XT uu = p.need_u ? uv[j] : (XT)1;
+        prod[j].v = p.flip ? MulApply<XT, ZT>::f(mul, uu, av) : MulApply<XT, ZT>::f(mul, av, uu);
+        prod[j].has = ok[j] && (!sparse_u || hs[j]);
+    }
+    group_barrier(bar_id, SPMV_THREADS);                          // head marks are complete
+
+    // ---- (3a) fold this thread's items between row marks
+    int32_t h[SPMV_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SPMV_ITEMS; j += 4) {
+        const int4 t4 = *reinterpret_cast<const int4 *>(&sm.headrow[loc0 + j]);
+        h[j] = t4.x; h[j + 1] = t4.y; h[j + 2] = t4.z; h[j + 3] = t4.w;
+    }
+    Part<ZT> acc{(ZT)0, 0}, lead{(ZT)0, 0};
+    bool seen = false; int32_t cur = -1;
+#pragma unroll
+    for (int j = 0; j < SPMV_ITEMS; ++j) {
+        if (h[j] >= 0) {
+            if (!seen) lead = acc;
+            else { tval[r0 + cur] = acc.v; p.tpres[r0 + cur] = (uint8_t)acc.has; }   // row began and ended in this thread
+            seen = true; cur = h[j]; acc.has = 0;
         }
-        if (lane == 0) emit(r, rs, re, acc, (uint8_t)has);
+        acc = part_join<ZT>(add, acc, prod[j]);
+    }
+    if (!seen) { lead = acc; acc.has = 0; }                        // no mark: everything continues an earlier row
+
+    // ---- (3b) segmented suffix scan of the leads: X_t = lead_t (+) (stop_t ? nothing : X_{t+1}), stop = thread has a mark
+    Part<ZT> x = lead; int stop = seen ? 1 : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Part<ZT> y; y.v = shfl_down_t<ZT>(x.v, d); y.has = __shfl_down_sync(0xffffffffu, x.has, d);
+        const int ystop = __shfl_down_sync(0xffffffffu, stop, d);
+        if (lane + d < 32) { if (!stop) x = part_join<ZT>(add, x, y); stop |= ystop; }
+    }
+    if (lane == 0) { sm.wv[warp] = x.v; sm.wflag[warp] = x.has | (stop << 1); }
+    group_barrier(bar_id, SPMV_THREADS);
+    // carry into this warp = what the following warps contribute to a segment still open at its end
+    Part<ZT> carry{(ZT)0, 0}; int carry_stop = 0;
+    for (int w = SPMV_WARPS - 1; w > warp; --w) {
+        Part<ZT> y; y.v = sm.wv[w]; const int f = sm.wflag[w]; y.has = f & 1;
+        const int ystop = f >> 1;
+        if (ystop) { carry = y; carry_stop = 1; } else carry = part_join<ZT>(add, y, carry);
+    }
+    if (!stop) { x = part_join<ZT>(add, x, carry); stop |= carry_stop; }
+    // S_t = X_{t+1}: what follows this thread's open row
+    Part<ZT> nxt; nxt.v = shfl_down_t<ZT>(x.v, 1); nxt.has = __shfl_down_sync(0xffffffffu, x.has, 1);
+    int nxt_stop = __shfl_down_sync(0xffffffffu, stop, 1);
+    if (lane == 31) { nxt = carry; nxt_stop = carry_stop; }
+
+    // ---- (4) rows still open at the end of a thread, and what sticks out of the tile
+    if (seen) {
+        const Part<ZT> total = part_join<ZT>(add, acc, nxt);
+        if (nxt_stop) { tval[r0 + cur] = total.v; p.tpres[r0 + cur] = (uint8_t)total.has; }
+        else { static_cast<ZT *>(p.tail_val)[tile] = total.v; p.tail_has[tile] = (uint8_t)total.has; p.tail_row[tile] = (int32_t)(r0 + cur); }
+    }
+    if (gtid == 0 && h[0] < 0) {                                   // the tile starts inside a row of an earlier tile
+        static_cast<ZT *>(p.head_val)[tile] = x.v; p.head_has[tile] = (uint8_t)x.has;
     }
 }
 
 // One CTA per tile (general path: any u, any semiring).
 template <typename XT, typename ZT, int ADD, int MUL>
 __global__ void __launch_bounds__(SPMV_THREADS, 5) spmv_tile_kernel(const SpmvArgs p) {
-    __shared__ ZT s_prod[SPMV_PROD_WORDS];
-    __shared__ uint8_t s_has[SPMV_PROD_WORDS];
-    __shared__ int s_queue[SPMV_QUEUE];
-    __shared__ int s_qcount;
-    const TileSmem<ZT> sm{s_prod, s_has, s_queue, &s_qcount};
+    __shared__ __align__(16) int32_t s_headrow[SPMV_TILE];
+    __shared__ ZT s_wv[SPMV_WARPS];
+    __shared__ int s_wflag[SPMV_WARPS];
+    const TileSmem<ZT> sm{s_headrow, s_wv, s_wflag};
     spmv_tile_body<XT, ZT, ADD, MUL, false>(p, blockIdx.x, sm, nullptr, 0u, threadIdx.x, 0);
 }
 
-// Persistent variant for dense u on large matrices: one 1024-thread CTA per SM = four independent
-// 256-thread groups striding over the tiles, all sharing a shared-memory table with the u values of
-// the hot_n most frequently referenced columns (the matrix's columns were relabelled by descending
-// in-degree, so "hot" is simply "id < hot_n").  On R-MAT graphs ~55-60% of all gathers hit the table,
-// which takes them off the L1TEX wavefront path that otherwise bounds the kernel.
+// Persistent variant for dense u on large matrices: HOT_GROUPS independent 256-thread groups per CTA
+// stride over the tiles, all sharing a shared-memory table with the u values of the hot_n most
+// frequently referenced columns (the matrix's columns were relabelled by descending in-degree, so
+// "hot" is simply "id < hot_n").  On R-MAT graphs half of all gathers hit the table.
 template <typename ZT> __host__ __device__ constexpr size_t hot_group_bytes() {
-    return ((SPMV_PROD_WORDS * sizeof(ZT) + (SPMV_QUEUE + 1) * sizeof(int)) + 15) & ~(size_t)15;
+    return ((SPMV_TILE * sizeof(int32_t) + SPMV_WARPS * (sizeof(ZT) + sizeof(int))) + 15) & ~(size_t)15;
 }
 template <typename XT, typename ZT, int ADD, int MUL, int HOT_GROUPS>
 __global__ void __launch_bounds__(SPMV_THREADS * HOT_GROUPS) spmv_hot_kernel(const SpmvArgs p, const uint32_t hot_n) {
@@ -272,10 +306,9 @@ __global__ void __launch_bounds__(SPMV_THREADS * HOT_GROUPS) spmv_hot_kernel(con
     const int group = threadIdx.x / SPMV_THREADS, gtid = threadIdx.x % SPMV_THREADS;
     unsigned char *gbase = smem_raw + (size_t)group * hot_group_bytes<ZT>();
     TileSmem<ZT> sm;
-    sm.prod = reinterpret_cast<ZT *>(gbase);
-    sm.has = nullptr;
-    sm.queue = reinterpret_cast<int *>(gbase + SPMV_PROD_WORDS * sizeof(ZT));
-    sm.qcount = sm.queue + SPMV_QUEUE;
+    sm.headrow = reinterpret_cast<int32_t *>(gbase);
+    sm.wv = reinterpret_cast<ZT *>(gbase + SPMV_TILE * sizeof(int32_t));
+    sm.wflag = reinterpret_cast<int *>(gbase + SPMV_TILE * sizeof(int32_t) + SPMV_WARPS * sizeof(ZT));
     XT *s_hot = reinterpret_cast<XT *>(smem_raw + HOT_GROUPS * hot_group_bytes<ZT>());
     const XT *uval = static_cast<const XT *>(p.uval);
     for (uint32_t i = threadIdx.x; i < hot_n; i += blockDim.x) s_hot[i] = uval[i];

@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Which part of the SpMV tile kernel costs what: same graph, semirings that drop the gather / the value stream."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import pygraphblas_b200 as gb
+from pygraphblas_b200 import Matrix, Vector, FP32
+from bench import cached_graph, spmv_inputs
+
+scale = int(sys.argv[1]) if len(sys.argv) > 1 else 22
+n, indptr, indices = cached_graph(scale)
+vals, u0 = spmv_inputs(scale, len(indices), n)
+A = Matrix.from_csr(indptr, indices, vals, n, n, FP32)
+u = Vector.from_numpy(u0)
+w = Vector.sparse(FP32, n)
+sp_ = gb.ffi.new("void**"); gb.lib.B200_get_stream(sp_)
+stream = torch.cuda.ExternalStream(int(gb.ffi.cast("uintptr_t", sp_[0])))
+
+def run(label, sr, env):
+    for k in ("B200GRB_NO_HOT", "B200GRB_HOT_GROUPS", "B200GRB_HOT_KB", "B200GRB_RELABEL_ONLY"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    for _ in range(5):
+        A.mxv(u, semiring=sr, out=w)
+    gb.lib.B200_device_synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(30):
+        A.mxv(u, semiring=sr, out=w)
+    e1.record(stream)
+    gb.lib.B200_device_synchronize(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 30
+    print(f"{label:44s} {ms*1e3:8.1f} us", flush=True)
+
+plain = {"B200GRB_NO_HOT": "1"}
+run("PLUS_TIMES  (col + val stream, gather)", FP32.PLUS_TIMES, plain)
+run("PLUS_SECOND (col stream, gather)", FP32.PLUS_SECOND, plain)
+run("PLUS_FIRST  (col + val stream, no gather)", FP32.PLUS_FIRST, plain)
+run("PLUS_PAIR   (col stream only)", FP32.PLUS_PAIR, plain)
+run("MIN_PLUS    (col + val stream, gather)", FP32.MIN_PLUS, plain)
+run("hot 128KB PLUS_TIMES", FP32.PLUS_TIMES, {"B200GRB_HOT_KB": "128"})
+run("hot 128KB PLUS_SECOND", FP32.PLUS_SECOND, {"B200GRB_HOT_KB": "128"})
