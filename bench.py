@@ -203,13 +203,10 @@ def run_b200(args):
         dist.barrier()
     nnz = len(indices)
     vals, u_host0 = spmv_inputs(args.scale, nnz, n)
-    from pygraphblas_b200.generators import row_block_bounds
-    bounds = row_block_bounds(indptr, world)
-    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
-    k0, k1 = int(indptr[r0]), int(indptr[r1])
-    lptr = (indptr[r0:r1 + 1] - k0).astype(np.int64)
-    A = Matrix.from_csr(lptr, indices[k0:k1], vals[k0:k1], r1 - r0, n, FP32)
-    lnnz, lrows = k1 - k0, r1 - r0
+    from pygraphblas_b200.distributed import local_block, allgather_slices
+    bounds, lptr, lidx, lval = local_block(indptr, indices, vals, world, rank)
+    lnnz, lrows = len(lidx), len(lptr) - 1
+    A = Matrix.from_csr(lptr, lidx, lval, lrows, n, FP32)
     u = Vector.from_numpy(u_host0)
     w = Vector.sparse(FP32, lrows)
     sr = FP32.PLUS_TIMES
@@ -217,7 +214,6 @@ def run_b200(args):
     if world > 1:
         uptr, _ = u.device_ptrs()
         u_t = torch.as_tensor(DevArray(uptr, n, "<f4"), device=torch.device("cuda", local))
-        slices = [u_t[int(bounds[r]):int(bounds[r + 1])] for r in range(world)]
 
     def step():
         A.mxv(u, semiring=sr, out=w)
@@ -225,7 +221,7 @@ def run_b200(args):
             wptr, _ = w.device_ptrs()
             w_t = torch.as_tensor(DevArray(wptr, lrows, "<f4"), device=torch.device("cuda", local))
             with torch.cuda.stream(stream):
-                dist.all_gather(slices, w_t)
+                allgather_slices(u_t, w_t, bounds)
 
     def sync_all():
         if world > 1:

@@ -1,0 +1,38 @@
+"""1-D row-block partitioning for the multi-GPU hot path.
+
+One process per GPU.  Rank r owns the contiguous row block [bounds[r], bounds[r+1]) of A, cut so
+that every block holds about the same number of entries (R-MAT hubs sit at low row ids, so equal-row
+splits are badly imbalanced).  `mxv` is local to the block; ONE all-gather of the output slices per
+operation gives every rank the full vector for the next one.  The collective runs through
+torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+import numpy as np
+
+from .generators import row_block_bounds
+
+
+def local_block(indptr, indices, values, world, rank):
+    """(bounds, local_indptr, local_indices, local_values) of rank's row block."""
+    bounds = row_block_bounds(indptr, world)
+    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    k0, k1 = int(indptr[r0]), int(indptr[r1])
+    lptr = (np.asarray(indptr[r0:r1 + 1]) - k0).astype(np.int64)
+    return bounds, lptr, indices[k0:k1], (None if values is None else values[k0:k1])
+
+
+def allgather_slices(full, local, bounds):
+    """All-gather the per-rank output slices `local` (uneven lengths) into the 1-D tensor `full`
+    (length bounds[-1]) on every rank.  `full` and `local` are torch tensors on the same device."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    views = [full[int(bounds[r]):int(bounds[r + 1])] for r in range(world)]
+    sizes = {v.numel() for v in views}
+    if len(sizes) == 1:
+        dist.all_gather(views, local)
+        return full
+    # uneven blocks (the normal case for nnz-balanced splits): one broadcast per owner, issued
+    # asynchronously so that NCCL can pipeline them on its stream
+    views[rank].copy_(local)
+    works = [dist.broadcast(views[r], src=r, async_op=True) for r in range(world) if views[r].numel()]
+    for w in works:
+        w.wait()
+    return full

@@ -1,0 +1,68 @@
+"""world_size-2 CPU (gloo) test of the multi-GPU host logic: nnz-balanced row blocks + one all-gather of
+the output slices reproduce the single-process SpMV.  The per-rank arithmetic here is the CPU oracle's
+OpenMP port (the CUDA kernels need a GPU); what is under test is the partition / gather plumbing that
+bench.py uses unchanged with NCCL."""
+import ctypes
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    from pygraphblas_b200.distributed import local_block, allgather_slices
+    from pygraphblas_b200.generators import rmat_csr
+    from oracle import oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, indptr, indices = rmat_csr(11, 8, seed=3)
+    rng = np.random.default_rng(0)
+    vals = (rng.integers(1, 9, len(indices)) / 4.0).astype(np.float32)
+    u = (rng.integers(0, 9, n) / 4.0).astype(np.float32)
+    bounds, lptr, lidx, lval = local_block(indptr, indices, vals, world, rank)
+    lrows = len(lptr) - 1
+    L = orc.lib()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    full = torch.from_numpy(u.copy())
+    for _ in range(3):                       # three chained steps: the gathered w is the next u
+        w = np.zeros(lrows, np.float32); pres = np.zeros(lrows, np.uint8)
+        uu = full.numpy()
+        L.fast_spmv_plus_times_f32(ctypes.c_int64(lrows), p(lptr), p(np.ascontiguousarray(lidx)), p(np.ascontiguousarray(lval)), p(uu), p(w), p(pres))
+        allgather_slices(full, torch.from_numpy(w), bounds)
+    if rank == 0:
+        np.save(out, full.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_block_allgather_world2(tmp_path):
+    import torch.multiprocessing as mp
+    from pygraphblas_b200.generators import rmat_csr, row_block_bounds
+    import scipy.sparse as sp
+    out = str(tmp_path / "w.npy")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    n, indptr, indices = rmat_csr(11, 8, seed=3)
+    rng = np.random.default_rng(0)
+    vals = (rng.integers(1, 9, len(indices)) / 4.0).astype(np.float32)
+    u = (rng.integers(0, 9, n) / 4.0).astype(np.float32)
+    A = sp.csr_matrix((vals.astype(np.float64), indices, indptr), shape=(n, n))
+    ref = u.astype(np.float64)
+    for _ in range(3):
+        ref = A @ ref
+    assert np.allclose(got, ref, rtol=1e-5)
+    # the split is nnz-balanced and covers every row exactly once
+    b = row_block_bounds(indptr, 8)
+    assert b[0] == 0 and b[-1] == n and np.all(np.diff(b) >= 0)
+    per = np.diff(indptr[b])
+    assert per.max() <= 1.3 * per.mean() + indptr[1:].max()
