@@ -58,10 +58,7 @@ struct Csr {
     // SpMV plan: first row of every TILE-sized slice of the nnz range (spmv.cu)
     uint32_t *tile_row = nullptr;
     int64_t ntiles = 0;
-    // hot-column plan (spmv.cu): columns relabelled by descending in-degree
-    uint32_t *hperm = nullptr;     // [hused] new id -> original column (columns that occur at least once)
-    uint32_t *hcol = nullptr;      // [nnz] relabelled column ids
-    int64_t hused = 0;
+    int tile_size = 0;
     bool valid = false;
 };
 

@@ -18,7 +18,7 @@ sp_ = gb.ffi.new("void**"); gb.lib.B200_get_stream(sp_)
 stream = torch.cuda.ExternalStream(int(gb.ffi.cast("uintptr_t", sp_[0])))
 
 def run(label, sr, env):
-    for k in ("B200GRB_NO_HOT", "B200GRB_HOT_GROUPS", "B200GRB_HOT_KB", "B200GRB_RELABEL_ONLY"):
+    for k in ("B200GRB_SPMV_ITEMS",):
         os.environ.pop(k, None)
     os.environ.update(env)
     for _ in range(5):
@@ -33,11 +33,11 @@ def run(label, sr, env):
     ms = e0.elapsed_time(e1) / 30
     print(f"{label:44s} {ms*1e3:8.1f} us", flush=True)
 
-plain = {"B200GRB_NO_HOT": "1"}
-run("PLUS_TIMES  (col + val stream, gather)", FP32.PLUS_TIMES, plain)
-run("PLUS_SECOND (col stream, gather)", FP32.PLUS_SECOND, plain)
-run("PLUS_FIRST  (col + val stream, no gather)", FP32.PLUS_FIRST, plain)
-run("PLUS_PAIR   (col stream only)", FP32.PLUS_PAIR, plain)
-run("MIN_PLUS    (col + val stream, gather)", FP32.MIN_PLUS, plain)
-run("hot 128KB PLUS_TIMES", FP32.PLUS_TIMES, {"B200GRB_HOT_KB": "128"})
-run("hot 128KB PLUS_SECOND", FP32.PLUS_SECOND, {"B200GRB_HOT_KB": "128"})
+for items in ("8", "16"):
+    env = {"B200GRB_SPMV_ITEMS": items}
+    run(f"items={items} PLUS_TIMES  (col + val stream, gather)", FP32.PLUS_TIMES, env)
+    run(f"items={items} PLUS_SECOND (col stream, gather)", FP32.PLUS_SECOND, env)
+    run(f"items={items} PLUS_FIRST  (col + val stream, no gather)", FP32.PLUS_FIRST, env)
+    run(f"items={items} PLUS_PAIR   (col stream only)", FP32.PLUS_PAIR, env)
+    run(f"items={items} MIN_PLUS", FP32.MIN_PLUS, env)
+run("run-time operators: PLUS_MINUS", FP32.PLUS_MINUS, {})

@@ -18,7 +18,7 @@ sp_ = gb.ffi.new("void**"); gb.lib.B200_get_stream(sp_)
 stream = torch.cuda.ExternalStream(int(gb.ffi.cast("uintptr_t", sp_[0])))
 
 def run(label, env):
-    for k in ("B200GRB_NO_HOT", "B200GRB_HOT_GROUPS", "B200GRB_HOT_KB", "B200GRB_RELABEL_ONLY"):
+    for k in ("B200GRB_SPMV_ITEMS",):
         os.environ.pop(k, None)
     os.environ.update(env)
     for _ in range(5):
