@@ -252,10 +252,25 @@ def test_rmat_masked_mxm_large_ST1_and_valued_mask():
     assert np.array_equal(Bp, R2.indptr) and np.array_equal(Bj, R2.indices) and np.array_equal(Bx, R2.data.astype(np.int64))
 
 
-def test_hot_column_spmv_matches_plain_kernel():
-    """Large dense-u SpMV takes the relabelled hot-column kernel; results must be bit-identical to the
-    plain tile kernel (same per-row product order), for specialised and run-time semirings."""
+@pytest.mark.parametrize("mode", [{}, {"B200GRB_SPMV_ITEMS": "16"}, {"B200GRB_SPMV_STREAM": "2"}, {"B200GRB_SPMV_STREAM": "3"}])
+def test_large_spmv_all_kernel_variants(mode):
+    """Large dense-u SpMV through every kernel variant (one CTA per tile with 8 / 16 entries per thread,
+    TMA-staged persistent kernel with 2 / 3 consumer groups): exact against the oracle on small-integer
+    data, for specialised and run-time semirings."""
     import os
+    old = {k: os.environ.get(k) for k in ("B200GRB_SPMV_ITEMS", "B200GRB_SPMV_STREAM")}
+    os.environ.update(mode)
+    try:
+        _large_spmv_body()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _large_spmv_body():
     n, indptr, indices = _rmat(17)
     assert len(indices) >= 1 << 20
     rng = np.random.default_rng(11)
