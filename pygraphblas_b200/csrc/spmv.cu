@@ -287,122 +287,6 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_tile_kernel(const SpmvArgs 
     spmv_tile_finish<XT, ZT, ADD, MUL, SPARSE, IT>(p, tile, tid, tlen, nvalid, c, a, s_head, s_wv, s_wflag, [] { __syncthreads(); });
 }
 
-// ---- TMA-staged persistent variant (dense u, specialised semirings)
-// One CTA per SM.  Warp 0 is the producer: a single lane streams the column / value words of the
-// CTA's tiles into a ring of shared-memory stages with cp.async.bulk (the TMA engine), completion
-// signalled through mbarriers.  STREAM_GROUPS consumer groups of 256 threads take the stages in turn,
-// copy their 8 entries each into registers, hand the stage back, and run the same gather / mark /
-// fold / scan as the general kernel.  The HBM stream is thereby decoupled from the consumers'
-// latency chain and no longer competes with the gathers for L1TEX request slots.
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) {} }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-static constexpr int STREAM_STAGES = 4;
-template <typename XT, typename ZT, bool NEED_A, int GROUPS> __host__ __device__ constexpr size_t stream_smem_bytes() {
-    constexpr size_t tile = SPMV_THREADS * 8;
-    return STREAM_STAGES * (tile * 4 + (NEED_A ? tile * sizeof(XT) : 0))            // ring: col (+ val) per stage
-           + GROUPS * (tile * 4 + SPMV_WARPS * 16)                                     // per group: head marks + scan aggregates
-           + 2 * STREAM_STAGES * 8 + 64;                                               // mbarriers
-}
-
-template <typename XT, typename ZT, int ADD, int MUL, int GROUPS>
-__global__ void __launch_bounds__(32 + SPMV_THREADS * GROUPS, 1) spmv_stream_kernel(const SpmvArgs p) {
-    constexpr int IT = 8;
-    constexpr int TILE = SPMV_THREADS * IT;
-    constexpr bool NEED_A = mul_reads_x(MUL);
-    constexpr size_t STAGE_BYTES = TILE * 4 + (NEED_A ? TILE * sizeof(XT) : 0);
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *ring = smem_raw;
-    unsigned char *gmem = ring + STREAM_STAGES * STAGE_BYTES;
-    uint64_t *full = reinterpret_cast<uint64_t *>(gmem + GROUPS * (TILE * 4 + SPMV_WARPS * 16));
-    uint64_t *empty = full + STREAM_STAGES;
-
-    const int64_t my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;   // tiles b, b+grid, ...
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STREAM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], SPMV_THREADS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (threadIdx.x < 32) {
-        // ---- producer warp: one lane drives the TMA engine
-        if (threadIdx.x == 0) {
-            for (int64_t i = 0; i < my_tiles; ++i) {
-                const int s = (int)(i % STREAM_STAGES);
-                const uint32_t par = (uint32_t)((i / STREAM_STAGES) & 1);
-                mbar_wait(&empty[s], par ^ 1u);                                   // stage free (passes at once the first time round)
-                const int64_t tile = blockIdx.x + i * (int64_t)gridDim.x;
-                const int64_t tstart = tile * TILE;
-                const uint32_t tlen = (uint32_t)min((int64_t)TILE, p.nnz - tstart);
-                const uint32_t cb = ((tlen * 4u) + 15u) & ~15u;
-                const uint32_t vb = NEED_A ? (((tlen * (uint32_t)sizeof(XT)) + 15u) & ~15u) : 0u;
-                unsigned char *dst = ring + (size_t)s * STAGE_BYTES;
-                mbar_expect_tx(&full[s], cb + vb);
-                bulk_g2s(dst, p.col + tstart, cb, &full[s]);
-                if (NEED_A) bulk_g2s(dst + TILE * 4, static_cast<const XT *>(p.aval) + tstart, vb, &full[s]);
-            }
-        }
-        return;
-    }
-
-    // ---- consumer groups
-    const int ct = threadIdx.x - 32;
-    const int group = ct / SPMV_THREADS, tid = ct % SPMV_THREADS;
-    unsigned char *gbase = gmem + (size_t)group * (TILE * 4 + SPMV_WARPS * 16);
-    int32_t *s_head = reinterpret_cast<int32_t *>(gbase);
-    ZT *s_wv = reinterpret_cast<ZT *>(gbase + TILE * 4);
-    int *s_wflag = reinterpret_cast<int *>(gbase + TILE * 4 + SPMV_WARPS * 8);
-    auto sync = [group] { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(SPMV_THREADS) : "memory"); };
-    for (int64_t i = group; i < my_tiles; i += GROUPS) {
-        const int s = (int)(i % STREAM_STAGES);
-        const uint32_t par = (uint32_t)((i / STREAM_STAGES) & 1);
-        const int64_t tile = blockIdx.x + i * (int64_t)gridDim.x;
-        const int64_t tstart = tile * TILE;
-        const int tlen = (int)min((int64_t)TILE, p.nnz - tstart);
-        const int loc0 = tid * IT;
-        const int nvalid = min(max(tlen - loc0, 0), IT);
-        mbar_wait(&full[s], par);                                                 // the stage's bytes have landed
-        const unsigned char *src = ring + (size_t)s * STAGE_BYTES;
-        uint32_t c[IT]; XT a[IT];
-        {
-            const uint4 c0 = *reinterpret_cast<const uint4 *>(src + (size_t)loc0 * 4);
-            const uint4 c1 = *reinterpret_cast<const uint4 *>(src + (size_t)loc0 * 4 + 16);
-            c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
-            if (NEED_A) {
-                const XT *av = reinterpret_cast<const XT *>(src + TILE * 4) + loc0;
-#pragma unroll
-                for (int j = 0; j < IT; ++j) a[j] = av[j];
-            }
-        }
-        if (nvalid < IT) {
-#pragma unroll
-            for (int j = 0; j < IT; ++j) { if (j >= nvalid) { c[j] = 0u; if (NEED_A) a[j] = (XT)1; } }
-        }
-        mbar_arrive(&empty[s]);                                                   // registers hold the entries: stage can be refilled
-        spmv_tile_finish<XT, ZT, ADD, MUL, false, IT>(p, (uint32_t)tile, tid, tlen, nvalid, c, a, s_head, s_wv, s_wflag, sync);
-        sync();                                                                   // group smem is reused by the next tile
-    }
-}
-
 // ---- fix-up: rows that straddle tiles = tail partial of the tile they start in
 //      (+) head partials of the following tiles, combined by one warp in a fixed order
 template <typename ZT, int ADD>
@@ -434,31 +318,12 @@ __global__ void clear_presence_kernel(uint8_t *p, int64_t n) {
 }
 
 static int g_items_fast = 8, g_items_generic = 8;     // entries per thread (tunable: B200GRB_SPMV_ITEMS)
-static int g_stream_groups = 0;                       // 0: one CTA per tile; 2/3: TMA-staged persistent kernel (B200GRB_SPMV_STREAM)
-
-template <typename XT, typename ZT, int ADD, int MUL, int GROUPS>
-static void spmv_stream_launch(const SpmvArgs &a) {
-    auto kernel = spmv_stream_kernel<XT, ZT, ADD, MUL, GROUPS>;
-    const size_t smem = stream_smem_bytes<XT, ZT, mul_reads_x(MUL), GROUPS>();
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int ctas = (int)std::min<int64_t>(G.num_sms, a.ntiles);
-    kernel<<<ctas, 32 + SPMV_THREADS * GROUPS, smem, G.stream>>>(a); GB_LAUNCHED();
-}
-
-template <typename XT, typename ZT, int ADD, int MUL, bool SPARSE, int IT>
-static void spmv_launch(const SpmvArgs &a) {
-    spmv_tile_kernel<XT, ZT, ADD, MUL, SPARSE, IT><<<(unsigned)a.ntiles, SPMV_THREADS, 0, G.stream>>>(a); GB_LAUNCHED();
-    spmv_fixup_kernel<ZT, ADD><<<(unsigned)ceil_div(a.ntiles * 32, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED();
-}
 
 // compile-time specialised semirings (BASELINE.json north_star: PLUS_TIMES, LOR_LAND, MIN_PLUS,
 // PLUS_SECOND; plus PLUS_PAIR / ANY_PAIR / PLUS_FIRST / MIN_FIRST / MIN_SECOND which the reference's
 // demos use) for dense u; everything else runs the same kernel with run-time operator codes.
 template <typename T> static bool spmv_fast(int add, int mul, int items, const SpmvArgs &a) {
-#define GB_FAST(A, M) if (add == A && mul == M) { \
-        if (items == 8 && g_stream_groups == 2) { spmv_stream_launch<T, T, A, M, 2>(a); spmv_fixup_kernel<T, A><<<(unsigned)ceil_div(a.ntiles * 32, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED(); } \
-        else if (items == 8 && g_stream_groups == 3) { spmv_stream_launch<T, T, A, M, 3>(a); spmv_fixup_kernel<T, A><<<(unsigned)ceil_div(a.ntiles * 32, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED(); } \
-        else if (items == 16) spmv_launch<T, T, A, M, false, 16>(a); else spmv_launch<T, T, A, M, false, 8>(a); return true; }
+#define GB_FAST(A, M) if (add == A && mul == M) { if (items == 16) spmv_launch<T, T, A, M, false, 16>(a); else spmv_launch<T, T, A, M, false, 8>(a); return true; }
     GB_FAST(OP_PLUS, OP_TIMES) GB_FAST(OP_MIN, OP_PLUS) GB_FAST(OP_PLUS, OP_SECOND) GB_FAST(OP_PLUS, OP_FIRST)
     GB_FAST(OP_PLUS, OP_PAIR) GB_FAST(OP_MIN, OP_FIRST) GB_FAST(OP_MIN, OP_SECOND)
 #undef GB_FAST
@@ -601,7 +466,6 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
     const bool sparse_u = u->dpres != nullptr;
     const bool fast = !kflip && spmv_is_fast(xt, zt, add, kmul, sparse_u);
     { const char *e = getenv("B200GRB_SPMV_ITEMS"); g_items_fast = (e && atoi(e) == 16) ? 16 : 8; }
-    { const char *e = getenv("B200GRB_SPMV_STREAM"); g_stream_groups = e ? atoi(e) : 0; }
     const int tile = SPMV_THREADS * (fast ? g_items_fast : g_items_generic);
     GB_TRY(spmv_plan(c, tile, err));
 

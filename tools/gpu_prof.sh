@@ -11,4 +11,4 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --c
     python tools/prof_spgemm.py ${SPGEMM_SCALE:-20} 1 masked > gpurun_out/ncu_launches2.log 2>&1; echo "launch list 2 rc=$?"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:masked_hash_kernel -c 2 -f -o gpurun_out/prof_mhash \
     python tools/prof_spgemm.py ${SPGEMM_SCALE:-20} 1 masked > gpurun_out/ncu_mhash.log 2>&1; echo "mhash capture rc=$?"
-ls -la gpurun_out
+ls -la gpurun_out | head -30

@@ -40,10 +40,4 @@ for items in ("8", "16"):
     run(f"items={items} PLUS_FIRST  (col + val stream, no gather)", FP32.PLUS_FIRST, env)
     run(f"items={items} PLUS_PAIR   (col stream only)", FP32.PLUS_PAIR, env)
     run(f"items={items} MIN_PLUS", FP32.MIN_PLUS, env)
-for g in ("2", "3"):
-    env = {"B200GRB_SPMV_STREAM": g}
-    run(f"stream groups={g} PLUS_TIMES", FP32.PLUS_TIMES, env)
-    run(f"stream groups={g} PLUS_SECOND", FP32.PLUS_SECOND, env)
-    run(f"stream groups={g} PLUS_FIRST (no gather)", FP32.PLUS_FIRST, env)
-    run(f"stream groups={g} PLUS_PAIR (col only)", FP32.PLUS_PAIR, env)
 run("run-time operators: PLUS_MINUS", FP32.PLUS_MINUS, {})
