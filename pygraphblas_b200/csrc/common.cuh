@@ -59,6 +59,10 @@ struct Csr {
     uint32_t *tile_row = nullptr;
     int64_t ntiles = 0;
     int tile_size = 0;
+    // hot-column plan (spmv.cu): columns relabelled by descending in-degree
+    uint32_t *hperm = nullptr;     // [ncols] new id -> original column
+    uint32_t *hcol = nullptr;      // [nnz] relabelled column ids
+    int64_t hused = 0;             // columns that occur at least once
     bool valid = false;
 };
 

@@ -83,6 +83,7 @@ __global__ void narrow_rowptr_kernel(const int64_t *rp, uint32_t *rp32, int64_t 
 GrB_Info dev_build_rowptr32(Csr &c, std::string *err) {
     dfree(c.rowptr32); c.rowptr32 = nullptr;
     dfree(c.tile_row); c.tile_row = nullptr; c.ntiles = 0; c.tile_size = 0;
+    dfree(c.hperm); dfree(c.hcol); c.hperm = nullptr; c.hcol = nullptr; c.hused = 0;
     if (c.nnz >= ((int64_t)1 << 32)) return GrB_SUCCESS;
     GB_TRY(dalloc(&c.rowptr32, (size_t)c.nrows + 1, err));
     const int64_t n = c.nrows + 1;
