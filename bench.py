@@ -126,6 +126,7 @@ class ClockSampler:
 def cpu_spmv(n, indptr, indices, vals, u, min_seconds, max_reps):
     from oracle import oracle as orc
     L = orc.lib()
+    L.fast_set_threads(ctypes.c_int(len(os.sched_getaffinity(0))))      # all host cores, whatever OMP_NUM_THREADS says
     L.fast_num_threads.restype = ctypes.c_int
     cores = L.fast_num_threads()
     w = np.zeros(n, np.float32)
@@ -388,6 +389,7 @@ def bench_spgemm(args, torch, stream, gb):
     # CPU port, one pass
     from oracle import oracle as orc
     Lc = orc.lib()
+    Lc.fast_set_threads(ctypes.c_int(len(os.sched_getaffinity(0))))
     cval = np.zeros(nnzL, np.int64)
     chas = np.zeros(nnzL, np.uint8)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)

@@ -16,6 +16,8 @@
 #include <omp.h>
 
 int fast_num_threads(void) { return omp_get_max_threads(); }
+/* use n threads (bench.py passes os.cpu_count(): torchrun exports OMP_NUM_THREADS=1) */
+void fast_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 /* w = A (+.x) u, PLUS_TIMES FP32, dense u; present[r] = row non-empty */
 void fast_spmv_plus_times_f32(int64_t nrows, const int64_t *ptr, const uint32_t *col, const float *val,

@@ -409,7 +409,7 @@ __device__ __forceinline__ void stream_b_rows(const GemmArgs &p, uint32_t pa0, u
 
 // Load-balanced streaming of the B rows named by A entries [c0, c1) for a whole CTA of NT threads:
 // NT entries at a time, the B-row lengths are prefix-summed in shared memory and the flattened
-// (entry, position) space is dealt out in runs of 4 consecutive positions per thread, so a hub B row
+// (entry, position) space is dealt out in runs of 8 consecutive positions per thread, so a hub B row
 // is spread over the whole CTA and short rows do not leave lanes idle.
 template <int NT, typename XT, typename Hit>
 __device__ __forceinline__ void flat_stream(const GemmArgs &p, uint32_t c0, uint32_t c1, uint32_t *s_off, uint32_t *s_bs, XT *s_av,
@@ -431,12 +431,13 @@ __device__ __forceinline__ void flat_stream(const GemmArgs &p, uint32_t c0, uint
         s_off[tid] = (uint32_t)off; s_bs[tid] = bs; s_av[tid] = av;
         __syncthreads();
         const int nent = (int)min((uint32_t)NT, c1 - base);
-        for (uint32_t f0 = (uint32_t)tid * 4u; f0 < (uint32_t)total; f0 += NT * 4u) {
+        constexpr uint32_t RUN = 8;
+        for (uint32_t f0 = (uint32_t)tid * RUN; f0 < (uint32_t)total; f0 += NT * RUN) {
             int lo = 0, hi = nent - 1;                       // largest e with s_off[e] <= f0
             while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= f0) lo = mid; else hi = mid - 1; }
             int e = lo;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (uint32_t i = 0; i < RUN; ++i) {
                 const uint32_t f = f0 + i;
                 if (f >= (uint32_t)total) break;
                 while (e + 1 < nent && s_off[e + 1] <= f) ++e;

@@ -472,7 +472,7 @@ static void spmv_launch(const SpmvArgs &a) {
 // PLUS_SECOND; plus PLUS_PAIR / ANY_PAIR / PLUS_FIRST / MIN_FIRST / MIN_SECOND which the reference's
 // demos use) for dense u; everything else runs the same kernel with run-time operator codes.
 template <typename T> static bool spmv_fast(int add, int mul, int items, const SpmvArgs &a) {
-#define GB_FAST(A, M) if (add == A && mul == M) { if (items == 16) spmv_launch<T, T, A, M, false, 16>(a); else spmv_launch<T, T, A, M, false, 8>(a); return true; }
+#define GB_FAST(A, M) if (add == A && mul == M) { if (items == 16) spmv_launch<T, T, A, M, false, 16>(a); else if (items == 4) spmv_launch<T, T, A, M, false, 4>(a); else spmv_launch<T, T, A, M, false, 8>(a); return true; }
     GB_FAST(OP_PLUS, OP_TIMES) GB_FAST(OP_MIN, OP_PLUS) GB_FAST(OP_PLUS, OP_SECOND) GB_FAST(OP_PLUS, OP_FIRST)
     GB_FAST(OP_PLUS, OP_PAIR) GB_FAST(OP_MIN, OP_FIRST) GB_FAST(OP_MIN, OP_SECOND)
 #undef GB_FAST
@@ -614,7 +614,7 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
     const bool need_u = kflip ? op_uses_x(kmul) : op_uses_y(kmul);
     const bool sparse_u = u->dpres != nullptr;
     const bool fast = !kflip && spmv_is_fast(xt, zt, add, kmul, sparse_u);
-    { const char *e = getenv("B200GRB_SPMV_ITEMS"); g_items_fast = (e && atoi(e) == 16) ? 16 : 8; }
+    { const char *e = getenv("B200GRB_SPMV_ITEMS"); const int v = e ? atoi(e) : 8; g_items_fast = (v == 16 || v == 4) ? v : 8; }
     const int tile = SPMV_THREADS * (fast ? g_items_fast : g_items_generic);
     GB_TRY(spmv_plan(c, tile, err));
 

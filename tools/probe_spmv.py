@@ -33,13 +33,7 @@ def run(label, sr, env):
     ms = e0.elapsed_time(e1) / 30
     print(f"{label:44s} {ms*1e3:8.1f} us", flush=True)
 
-for groups in ("4", "2"):
-    for kb in ("16", "32", "64", "96", "128", "160"):
-        env = {"B200GRB_SPMV_HOT": kb, "B200GRB_HOT_GROUPS": groups}
-        run(f"hot groups={groups} table={kb}KB PLUS_TIMES", FP32.PLUS_TIMES, env)
-run("hot groups=4 table=128KB PLUS_SECOND", FP32.PLUS_SECOND, {"B200GRB_SPMV_HOT": "128"})
-run("hot groups=4 table=128KB MIN_PLUS", FP32.MIN_PLUS, {"B200GRB_SPMV_HOT": "128"})
-for items in ("8",):
+for items in ("4", "8"):
     env = {"B200GRB_SPMV_ITEMS": items}
     run(f"items={items} PLUS_TIMES  (col + val stream, gather)", FP32.PLUS_TIMES, env)
     run(f"items={items} PLUS_SECOND (col stream, gather)", FP32.PLUS_SECOND, env)
