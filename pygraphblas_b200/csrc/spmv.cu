@@ -25,6 +25,11 @@
 
 GrB_Info dev_exclusive_scan(int64_t *data, int64_t n, std::string *err);
 
+// build with -DB200GRB_PHASE_TIMERS=1 and run with B200GRB_SPMV_DEBUG=1 to get per-phase cycle counts of the tile kernel
+#ifndef B200GRB_PHASE_TIMERS
+#define B200GRB_PHASE_TIMERS 0
+#endif
+static constexpr bool SPMV_PHASE_TIMERS = B200GRB_PHASE_TIMERS != 0;
 static constexpr int SPMV_THREADS = 256;
 static constexpr int SPMV_WARPS = SPMV_THREADS / 32;
 
@@ -37,6 +42,7 @@ struct SpmvArgs {
     int add_op, mul_op;
     int flip;      // 0: z = mul(a, u) (mxv)   1: z = mul(u, a) (vxm)   (run-time-operator kernels only)
     int tile;      // entries per tile = SPMV_THREADS * items per thread
+    unsigned long long *dbg;   // optional per-phase cycle counters (B200GRB_SPMV_DEBUG), nullptr in production
 };
 
 // ---- plan: tile_row[t] = row holding entry t*tile (tile_row[0] = 0, tile_row[ntiles] = nrows)
@@ -153,6 +159,8 @@ __device__ __forceinline__ void spmv_tile_finish(const SpmvArgs &p, const uint32
     const XT *uval = static_cast<const XT *>(p.uval);
     ZT *tval = static_cast<ZT *>(p.tval);
 
+    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    if (SPMV_PHASE_TIMERS && p.dbg && tid == 0) t0 = clock64();
     const uint32_t r0 = p.tile_row[tile];
     const uint32_t r1 = (uint32_t)min((int64_t)p.tile_row[tile + 1], p.nrows - 1);
     uint32_t pre_rs = 0, pre_re = 0;                                      // row pointers of this thread's first row
@@ -173,6 +181,7 @@ __device__ __forceinline__ void spmv_tile_finish(const SpmvArgs &p, const uint32
         }
     }
     sync();                                                               // head marks are clear
+    if (SPMV_PHASE_TIMERS && p.dbg && tid == 0) t1 = clock64();
 
     // ---- (2) rows of the tile: empty ones are final, the others mark their first entry
     {
@@ -193,6 +202,7 @@ __device__ __forceinline__ void spmv_tile_finish(const SpmvArgs &p, const uint32
         else prod[j] = p.flip ? MulApply<XT, ZT>::f(mul, uu, av) : MulApply<XT, ZT>::f(mul, av, uu);
     }
     sync();                                                               // head marks are complete
+    if (SPMV_PHASE_TIMERS && p.dbg && tid == 0) t2 = clock64();
 
     // ---- (3a) fold this thread's items between row marks
     int32_t h[IT];
@@ -238,6 +248,7 @@ __device__ __forceinline__ void spmv_tile_finish(const SpmvArgs &p, const uint32
     }
     if (lane == 0) { s_wv[warp] = x.v; s_wflag[warp] = x.has | (stop << 1); }
     sync();
+    if (SPMV_PHASE_TIMERS && p.dbg && tid == 0) t3 = clock64();
     Part<ZT> carry{(ZT)0, 0}; int carry_stop = 0;                         // what the following warps add to a row open at this warp's end
     for (int w = SPMV_WARPS - 1; w > warp; --w) {
         Part<ZT> y; y.v = s_wv[w]; const int f = s_wflag[w]; y.has = f & 1;
@@ -256,6 +267,12 @@ __device__ __forceinline__ void spmv_tile_finish(const SpmvArgs &p, const uint32
     }
     if (tid == 0 && h[0] < 0) {                                           // the tile starts inside a row of an earlier tile
         static_cast<ZT *>(p.head_val)[tile] = x.v; p.head_has[tile] = (uint8_t)x.has;
+    }
+    if (SPMV_PHASE_TIMERS && p.dbg && tid == 0) {
+        const long long t4 = clock64();
+        atomicAdd(&p.dbg[0], (unsigned long long)(t1 - t0)); atomicAdd(&p.dbg[1], (unsigned long long)(t2 - t1));
+        atomicAdd(&p.dbg[2], (unsigned long long)(t3 - t2)); atomicAdd(&p.dbg[3], (unsigned long long)(t4 - t3));
+        atomicAdd(&p.dbg[4], 1ull);
     }
 }
 
@@ -300,7 +317,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_tile_kernel(const SpmvArgs 
 // the tiles (on R-MAT graphs the top 32 K of 4 M columns take 53 % of all gathers).
 template <typename ZT> __host__ __device__ constexpr size_t hot_group_bytes() { return SPMV_THREADS * 8 * 4 + SPMV_WARPS * 16; }
 template <typename XT, typename ZT, int ADD, int MUL, int GROUPS>
-__global__ void __launch_bounds__(SPMV_THREADS * GROUPS, 1) spmv_hot_kernel(const SpmvArgs p, const uint32_t hot_n) {
+__global__ void __launch_bounds__(SPMV_THREADS * GROUPS, (GROUPS == 4 ? 1 : (GROUPS == 3 ? 2 : (GROUPS == 2 ? 3 : 6)))) spmv_hot_kernel(const SpmvArgs p, const uint32_t hot_n) {
     constexpr int IT = 8;
     constexpr int TILE = SPMV_THREADS * IT;
     constexpr bool NEED_A = mul_reads_x(MUL);
@@ -459,7 +476,10 @@ template <typename XT, typename ZT, int ADD, int MUL, bool SPARSE, int IT>
 static void spmv_launch(const SpmvArgs &a) {
     if constexpr (ADD >= 0 && !SPARSE && IT == 8) {
         if (g_hot.on) {
-            if (g_hot.groups == 2) spmv_hot_launch<XT, ZT, ADD, MUL, 2>(a, g_hot); else spmv_hot_launch<XT, ZT, ADD, MUL, 4>(a, g_hot);
+            if (g_hot.groups == 1) spmv_hot_launch<XT, ZT, ADD, MUL, 1>(a, g_hot);
+            else if (g_hot.groups == 2) spmv_hot_launch<XT, ZT, ADD, MUL, 2>(a, g_hot);
+            else if (g_hot.groups == 3) spmv_hot_launch<XT, ZT, ADD, MUL, 3>(a, g_hot);
+            else spmv_hot_launch<XT, ZT, ADD, MUL, 4>(a, g_hot);
             spmv_fixup_kernel<ZT, ADD><<<(unsigned)ceil_div(a.ntiles * 32, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED();
             return;
         }
@@ -657,7 +677,15 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
             g_hot.on = true; g_hot.hused = c.hused; g_hot.table_bytes = (size_t)atoi(hot_env) << 10;
             if (const char *e = getenv("B200GRB_HOT_GROUPS")) g_hot.groups = atoi(e); else g_hot.groups = 4;
         }
+        if (SPMV_PHASE_TIMERS && getenv("B200GRB_SPMV_DEBUG")) { GB_TRY(dalloc(&a.dbg, 8, err)); CU_TRY(cudaMemsetAsync(a.dbg, 0, 64, G.stream), err); }
         GrB_Info r = spmv_dispatch(xt, zt, add, kmul, sparse_u, a, err);
+        if (a.dbg) {
+            unsigned long long h[5];
+            cudaMemcpyAsync(h, a.dbg, 40, cudaMemcpyDeviceToHost, G.stream); cudaStreamSynchronize(G.stream);
+            if (h[4]) fprintf(stderr, "[spmv phases, avg cycles per tile] load+issue %.0f | rows+gather %.0f | fold+scan %.0f | carry+store %.0f | tiles %llu\n",
+                              (double)h[0] / h[4], (double)h[1] / h[4], (double)h[2] / h[4], (double)h[3] / h[4], h[4]);
+            dfree(a.dbg);
+        }
         g_hot.on = false;
         dfree(u_perm);
         dfree(a.head_val); dfree(a.tail_val); dfree(a.head_has); dfree(a.tail_has); dfree(a.tail_row);

@@ -18,7 +18,7 @@ sp_ = gb.ffi.new("void**"); gb.lib.B200_get_stream(sp_)
 stream = torch.cuda.ExternalStream(int(gb.ffi.cast("uintptr_t", sp_[0])))
 
 def run(label, sr, env):
-    for k in ("B200GRB_SPMV_ITEMS", "B200GRB_SPMV_HOT", "B200GRB_HOT_GROUPS"):
+    for k in ("B200GRB_SPMV_ITEMS", "B200GRB_SPMV_HOT", "B200GRB_HOT_GROUPS", "B200GRB_SPMV_DEBUG"):
         os.environ.pop(k, None)
     os.environ.update(env)
     for _ in range(5):
@@ -33,7 +33,10 @@ def run(label, sr, env):
     ms = e0.elapsed_time(e1) / 30
     print(f"{label:44s} {ms*1e3:8.1f} us", flush=True)
 
-for items in ("4", "8"):
+for kb in ("1", "4", "8", "16"):
+    run(f"persistent groups=1 table={kb}KB PLUS_TIMES", FP32.PLUS_TIMES, {"B200GRB_SPMV_HOT": kb, "B200GRB_HOT_GROUPS": "1"})
+run("persistent groups=1 table=1KB MIN_PLUS", FP32.MIN_PLUS, {"B200GRB_SPMV_HOT": "1", "B200GRB_HOT_GROUPS": "1"})
+for items in ("8",):
     env = {"B200GRB_SPMV_ITEMS": items}
     run(f"items={items} PLUS_TIMES  (col + val stream, gather)", FP32.PLUS_TIMES, env)
     run(f"items={items} PLUS_SECOND (col stream, gather)", FP32.PLUS_SECOND, env)
