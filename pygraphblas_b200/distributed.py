@@ -29,10 +29,17 @@ def allgather_slices(full, local, bounds):
     if len(sizes) == 1:
         dist.all_gather(views, local)
         return full
-    # uneven blocks (the normal case for nnz-balanced splits): one broadcast per owner, issued
-    # asynchronously so that NCCL can pipeline them on its stream
+    # uneven blocks (the normal case for nnz-balanced splits): every rank sends its slice to every
+    # peer and receives theirs, batched into ONE grouped NCCL operation (all-gather-v)
     views[rank].copy_(local)
-    works = [dist.broadcast(views[r], src=r, async_op=True) for r in range(world) if views[r].numel()]
-    for w in works:
+    ops = []
+    for r in range(world):
+        if r == rank:
+            continue
+        if local.numel():
+            ops.append(dist.P2POp(dist.isend, local, r))
+        if views[r].numel():
+            ops.append(dist.P2POp(dist.irecv, views[r], r))
+    for w in dist.batch_isend_irecv(ops) if ops else []:
         w.wait()
     return full
