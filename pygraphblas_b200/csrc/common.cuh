@@ -59,6 +59,13 @@ struct Csr {
     uint32_t *tile_row = nullptr;
     int64_t ntiles = 0;
     int tile_size = 0;
+    // run plan (spmv.cu, dense-u kernel): entries cut into warp-sized runs of 256
+    uint32_t *run_headw = nullptr;   // [ceil(nnz/32)] bit q = entry q starts a row
+    uint16_t *run_lane = nullptr;    // [nruns*32] row starts inside the run before the lane's first entry
+    uint32_t *run_base = nullptr;    // [nruns] row starts before the run (= rank of its first row start)
+    uint32_t *nzrow = nullptr;       // [nnzrows] ids of the non-empty rows, ascending
+    uint8_t *pres_tmpl = nullptr;    // [nrows] 1 where the row is non-empty
+    int64_t nruns = 0, nnzrows = 0;
     // hot-column plan (spmv.cu): columns relabelled by descending in-degree
     uint32_t *hperm = nullptr;     // [ncols] new id -> original column
     uint32_t *hcol = nullptr;      // [nnz] relabelled column ids

@@ -372,6 +372,269 @@ __global__ void permute_u_kernel(const uint32_t *perm, const uint8_t *u, uint8_t
 }
 
 
+// ==================================================================================================
+// Dense-u kernel for the specialised semirings: warp-independent RUNS.
+//
+// The entries are cut into runs of 256 (one warp, 8 consecutive entries per lane).  A cached plan gives
+// every lane what the tile kernel has to discover with shared-memory marks, a row pass and barriers:
+//   run_headw   one bit per entry: "this entry starts a row"
+//   run_base    number of row starts before the run;  run_lane: row starts inside the run before the lane
+//   nzrow       ids of the non-empty rows (row start rank -> row id);  pres_tmpl: the output's presence
+// so a warp needs no shared memory and no barrier: stream 8 entries, gather, fold between the row-start
+// bits (rows inside a lane are final), one segmented suffix scan over the 32 lanes, and the two partial
+// rows sticking out of the run go to per-run slots that spmv_run_fixup_kernel combines in a fixed order
+// (deterministic).  ~3.5x fewer instructions per entry than the tile kernel.
+// HOT: persistent CTAs, hot_n most referenced entries of the (relabelled) u in a shared-memory table.
+static constexpr int RUN = 256;
+
+struct RunArgs {
+    const uint32_t *col; const void *aval; const void *uval;
+    const uint32_t *headw; const uint16_t *lane_rank; const uint32_t *run_base; const uint32_t *nzrow; const uint32_t *rowptr;
+    int64_t nruns; int64_t nnz;
+    void *tval;
+    void *head_val; uint8_t *head_has; void *tail_val; int32_t *tail_rank;
+};
+
+template <typename XT, typename ZT, int ADD, int MUL, bool HOT>
+__device__ __forceinline__ void spmv_run_body(const RunArgs &p, const int64_t run, const int lane, const XT *s_hot, const uint32_t hot_n) {
+    constexpr bool NEED_A = mul_reads_x(MUL);
+    constexpr bool NEED_U = mul_reads_y(MUL);
+    const int64_t q = run * RUN + lane * 8;
+    const int nvalid = (int)min((int64_t)8, max((int64_t)0, p.nnz - q));
+    const XT *uval = static_cast<const XT *>(p.uval);
+    ZT *tval = static_cast<ZT *>(p.tval);
+    uint32_t c[8]; XT a[8];
+    if (nvalid == 8) {
+        load4<uint32_t>(p.col + q, &c[0]); load4<uint32_t>(p.col + q + 4, &c[4]);
+        if (NEED_A) { load4<XT>(static_cast<const XT *>(p.aval) + q, &a[0]); load4<XT>(static_cast<const XT *>(p.aval) + q + 4, &a[4]); }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            c[j] = j < nvalid ? p.col[q + j] : 0u;
+            if (NEED_A) a[j] = j < nvalid ? static_cast<const XT *>(p.aval)[q + j] : (XT)1;
+        }
+    }
+    const uint32_t hw = nvalid > 0 ? __ldg(p.headw + (q >> 5)) : 0u;
+    const uint32_t hb = (hw >> ((lane & 3) * 8)) & 0xffu;                 // this lane's 8 row-start bits
+    uint32_t rank = __ldg(p.run_base + run) + __ldg(p.lane_rank + run * 32 + lane);   // row starts before this lane's first entry
+    XT uv[8];
+    if (NEED_U) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (HOT && c[j] < hot_n) uv[j] = s_hot[c[j]];
+            else uv[j] = gload<XT>(uval + c[j]);
+        }
+    }
+    ZT prod[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) prod[j] = MulApply<XT, ZT>::f(MUL, NEED_A ? a[j] : (XT)1, NEED_U ? uv[j] : (XT)1);
+
+    // ---- fold between row starts
+    Part<ZT> acc{(ZT)0, 0}, lead{(ZT)0, 0};
+    bool seen = false; uint32_t cur = 0;
+    if (nvalid == 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if ((hb >> j) & 1u) {
+                if (!seen) lead = acc;
+                else tval[__ldg(p.nzrow + cur)] = acc.v;                    // row began and ended inside this lane
+                seen = true; cur = rank++; acc.v = prod[j]; acc.has = 1;
+            } else if (j == 0) { acc.v = prod[0]; acc.has = 1; }
+            else acc.v = MulApply<ZT, ZT>::f(ADD, acc.v, prod[j]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < nvalid) {
+                if ((hb >> j) & 1u) {
+                    if (!seen) lead = acc;
+                    else tval[__ldg(p.nzrow + cur)] = acc.v;
+                    seen = true; cur = rank++; acc.has = 0;
+                }
+                const Part<ZT> it{prod[j], 1};
+                acc = part_join<ZT>(ADD, acc, it);
+            }
+        }
+    }
+    if (!seen) { lead = acc; acc.has = 0; }
+
+    // ---- segmented suffix scan of the leads over the 32 lanes
+    Part<ZT> x = lead; int stop = seen ? 1 : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Part<ZT> y; y.v = shfl_down_t<ZT>(x.v, d);
+        const int yf = __shfl_down_sync(0xffffffffu, x.has | (stop << 1), d);
+        y.has = yf & 1;
+        if (lane + d < 32) { if (!stop) x = part_join<ZT>(ADD, x, y); stop |= yf >> 1; }
+    }
+    Part<ZT> nxt; nxt.v = shfl_down_t<ZT>(x.v, 1);
+    const int nf = __shfl_down_sync(0xffffffffu, x.has | (stop << 1), 1);
+    nxt.has = nf & 1; int nxt_stop = nf >> 1;
+    if (lane == 31) { nxt.has = 0; nxt_stop = 0; }
+
+    // the lane holding the last row start of the run owns the row that is still open at the run's end
+    const bool open_tail = seen && !nxt_stop;
+    if (seen) {
+        const Part<ZT> total = part_join<ZT>(ADD, acc, nxt);
+        if (nxt_stop) tval[__ldg(p.nzrow + cur)] = total.v;
+        else { static_cast<ZT *>(p.tail_val)[run] = total.v; p.tail_rank[run] = (int32_t)cur; }
+    }
+    const unsigned any_tail = __ballot_sync(0xffffffffu, open_tail);
+    if (lane == 0) {
+        const bool inside = !(hb & 1u) && nvalid > 0;                       // the run starts inside a row of an earlier run
+        if (inside) static_cast<ZT *>(p.head_val)[run] = x.v;
+        p.head_has[run] = inside ? (uint8_t)x.has : (uint8_t)0;
+        if (!any_tail) p.tail_rank[run] = -1;
+    }
+}
+
+template <typename XT, typename ZT, int ADD, int MUL>
+__global__ void __launch_bounds__(256) spmv_run_kernel(const RunArgs p) {
+    const int64_t run = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (run >= p.nruns) return;
+    spmv_run_body<XT, ZT, ADD, MUL, false>(p, run, threadIdx.x & 31, nullptr, 0u);
+}
+
+template <typename XT, typename ZT, int ADD, int MUL>
+__global__ void __launch_bounds__(1024, 1) spmv_run_hot_kernel(const RunArgs p, const uint32_t hot_n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    XT *s_hot = reinterpret_cast<XT *>(smem_raw);
+    const XT *uval = static_cast<const XT *>(p.uval);
+    for (uint32_t i = threadIdx.x; i < hot_n; i += blockDim.x) s_hot[i] = uval[i];
+    __syncthreads();
+    const int warps = blockDim.x >> 5;
+    for (int64_t run = (int64_t)blockIdx.x * warps + (threadIdx.x >> 5); run < p.nruns; run += (int64_t)gridDim.x * warps)
+        spmv_run_body<XT, ZT, ADD, MUL, true>(p, run, threadIdx.x & 31, s_hot, hot_n);
+}
+
+// rows that continue past their run: tail partial (+) head partials of the following runs, 8 lanes per open row
+template <typename ZT, int ADD>
+__global__ void __launch_bounds__(256) spmv_run_fixup_kernel(const RunArgs p) {
+    const int sub = threadIdx.x & 7;
+    const int64_t run = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool active = run < p.nruns;
+    int32_t rk = active ? p.tail_rank[run] : -1;
+    // all 8 lanes of a group take the same branch; shuffles below use the full mask with width 8
+    Part<ZT> acc{(ZT)0, 0};
+    uint32_t r = 0;
+    if (rk >= 0) {
+        r = p.nzrow[rk];
+        const int64_t last_run = ((int64_t)p.rowptr[r + 1] - 1) / RUN;
+        if (sub == 0) { acc.v = static_cast<const ZT *>(p.tail_val)[run]; acc.has = 1; }
+        for (int64_t t = run + 1 + sub; t <= last_run; t += 8) if (p.head_has[t]) {
+            const Part<ZT> y{static_cast<const ZT *>(p.head_val)[t], 1};
+            acc = part_join<ZT>(ADD, acc, y);
+        }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        Part<ZT> y; y.v = shfl_xor_t<ZT>(acc.v, o); y.has = __shfl_xor_sync(0xffffffffu, acc.has, o);
+        acc = part_join<ZT>(ADD, acc, y);
+    }
+    if (rk >= 0 && sub == 0) static_cast<ZT *>(p.tval)[r] = acc.v;
+}
+
+// ---- run plan (cached per CSR)
+__global__ void plan_nonempty_kernel(const uint32_t *rowptr, int64_t nrows, int64_t *flag, uint8_t *pres) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int ne = rowptr[r + 1] > rowptr[r];
+        flag[r] = ne; pres[r] = (uint8_t)ne;
+    }
+}
+__global__ void plan_rows_kernel(const uint32_t *rowptr, const int64_t *rank, int64_t nrows, uint32_t *nzrow, uint32_t *headw) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t rs = rowptr[r];
+        if (rowptr[r + 1] > rs) { nzrow[rank[r]] = (uint32_t)r; atomicOr(&headw[rs >> 5], 1u << (rs & 31)); }
+    }
+}
+__global__ void plan_runs_kernel(const uint32_t *headw, int64_t nruns, int64_t nwords, uint16_t *lane_rank, int64_t *run_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t run = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (run >= nruns) return;
+    const int64_t w = run * 8 + (lane >> 2);
+    const uint32_t hw = w < nwords ? headw[w] : 0u;
+    const int pc = __popc((hw >> ((lane & 3) * 8)) & 0xffu);
+    int inc = pc;
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    lane_rank[run * 32 + lane] = (uint16_t)(inc - pc);
+    if (lane == 31) run_cnt[run] = inc;
+}
+__global__ void plan_base_kernel(const int64_t *scan, int64_t nruns, uint32_t *run_base) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nruns; k += (int64_t)gridDim.x * blockDim.x) run_base[k] = (uint32_t)scan[k];
+}
+static inline int rgrid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), (int64_t)G.num_sms * 16)); }
+
+static GrB_Info spmv_run_plan(Csr &c, std::string *err) {
+    if (c.run_headw) return GrB_SUCCESS;
+    if (!c.rowptr32) return gb_fail(GrB_INVALID_VALUE, err, "mxv: matrices with >= 2^32 entries are not supported");
+    const int64_t nwords = ceil_div(c.nnz, 32);
+    c.nruns = ceil_div(c.nnz, RUN);
+    int64_t *flag = nullptr, *cnt = nullptr;
+    GB_TRY(dalloc(&flag, (size_t)c.nrows + 1, err));
+    GB_TRY(dalloc(&cnt, (size_t)c.nruns + 1, err));
+    GB_TRY(dalloc(&c.pres_tmpl, (size_t)c.nrows, err));
+    GB_TRY(dalloc(&c.run_headw, (size_t)nwords + 8, err));
+    GB_TRY(dalloc(&c.run_lane, (size_t)c.nruns * 32, err));
+    GB_TRY(dalloc(&c.run_base, (size_t)c.nruns, err));
+    CU_TRY(cudaMemsetAsync(c.run_headw, 0, ((size_t)nwords + 8) * 4, G.stream), err);
+    CU_TRY(cudaMemsetAsync(flag + c.nrows, 0, 8, G.stream), err);
+    plan_nonempty_kernel<<<rgrid(c.nrows), 256, 0, G.stream>>>(c.rowptr32, c.nrows, flag, c.pres_tmpl); GB_LAUNCHED();
+    GB_TRY(dev_exclusive_scan(flag, c.nrows + 1, err));
+    int64_t nz = 0;
+    CU_TRY(cudaMemcpyAsync(&nz, flag + c.nrows, 8, cudaMemcpyDeviceToHost, G.stream), err);
+    CU_TRY(cudaStreamSynchronize(G.stream), err);
+    c.nnzrows = nz;
+    GB_TRY(dalloc(&c.nzrow, (size_t)nz, err));
+    plan_rows_kernel<<<rgrid(c.nrows), 256, 0, G.stream>>>(c.rowptr32, flag, c.nrows, c.nzrow, c.run_headw); GB_LAUNCHED();
+    CU_TRY(cudaMemsetAsync(cnt + c.nruns, 0, 8, G.stream), err);
+    plan_runs_kernel<<<(unsigned)ceil_div(c.nruns * 32, 256), 256, 0, G.stream>>>(c.run_headw, c.nruns, nwords, c.run_lane, cnt); GB_LAUNCHED();
+    GB_TRY(dev_exclusive_scan(cnt, c.nruns + 1, err));
+    plan_base_kernel<<<rgrid(c.nruns), 256, 0, G.stream>>>(cnt, c.nruns, c.run_base); GB_LAUNCHED();
+    dfree(flag); dfree(cnt);
+    CU_TRY(cudaGetLastError(), err);
+    return GrB_SUCCESS;
+}
+
+template <typename XT, typename ZT, int ADD, int MUL>
+static void spmv_run_launch(const RunArgs &a, size_t hot_bytes, int64_t hused) {
+    if (hot_bytes) {
+        auto kernel = spmv_run_hot_kernel<XT, ZT, ADD, MUL>;
+        const uint32_t hot_n = (uint32_t)std::min<int64_t>(hused, (int64_t)(hot_bytes / sizeof(XT)));
+        const size_t smem = (size_t)hot_n * sizeof(XT);
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kernel<<<G.num_sms, 1024, smem, G.stream>>>(a, hot_n); GB_LAUNCHED();
+    } else {
+        spmv_run_kernel<XT, ZT, ADD, MUL><<<(unsigned)ceil_div(a.nruns, 8), 256, 0, G.stream>>>(a); GB_LAUNCHED();
+    }
+    spmv_run_fixup_kernel<ZT, ADD><<<(unsigned)ceil_div(a.nruns * 8, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED();
+}
+
+template <typename T> static bool spmv_run_fast(int add, int mul, const RunArgs &a, size_t hot_bytes, int64_t hused) {
+#define GB_FAST(A, M) if (add == A && mul == M) { spmv_run_launch<T, T, A, M>(a, hot_bytes, hused); return true; }
+    GB_FAST(OP_PLUS, OP_TIMES) GB_FAST(OP_MIN, OP_PLUS) GB_FAST(OP_PLUS, OP_SECOND) GB_FAST(OP_PLUS, OP_FIRST)
+    GB_FAST(OP_PLUS, OP_PAIR) GB_FAST(OP_MIN, OP_FIRST) GB_FAST(OP_MIN, OP_SECOND)
+#undef GB_FAST
+    return false;
+}
+static bool spmv_run_fast_bool(int add, int mul, const RunArgs &a, size_t hot_bytes, int64_t hused) {
+#define GB_FAST(A, M) if (add == A && mul == M) { spmv_run_launch<bool, bool, A, M>(a, hot_bytes, hused); return true; }
+    GB_FAST(OP_LOR, OP_LAND) GB_FAST(OP_ANY, OP_PAIR) GB_FAST(OP_LOR, OP_PAIR) GB_FAST(OP_LOR, OP_SECOND) GB_FAST(OP_LOR, OP_FIRST)
+#undef GB_FAST
+    return false;
+}
+static bool spmv_run_dispatch(int xt, int add, int mul, const RunArgs &a, size_t hot_bytes, int64_t hused) {
+    switch (xt) {
+        case TC_FP32: return spmv_run_fast<float>(add, mul, a, hot_bytes, hused);
+        case TC_FP64: return spmv_run_fast<double>(add, mul, a, hot_bytes, hused);
+        case TC_INT32: return spmv_run_fast<int32_t>(add, mul, a, hot_bytes, hused);
+        case TC_INT64: return spmv_run_fast<int64_t>(add, mul, a, hot_bytes, hused);
+        case TC_UINT32: return spmv_run_fast<uint32_t>(add, mul, a, hot_bytes, hused);
+        case TC_UINT64: return spmv_run_fast<uint64_t>(add, mul, a, hot_bytes, hused);
+        case TC_BOOL: return spmv_run_fast_bool(add, mul, a, hot_bytes, hused);
+        default: return false;
+    }
+}
+
 // ---- fix-up: rows that straddle tiles = tail partial of the tile they start in
 //      (+) head partials of the following tiles, combined by one warp in a fixed order
 template <typename ZT, int ADD>
@@ -652,7 +915,33 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
     GB_TRY(dmalloc(&tval, (size_t)n * zsz + 16, err));
     GB_TRY(dmalloc((void **)&tpres, (size_t)n + 16, err));
 
-    if (c.nnz == 0) {
+    // dense u + specialised semiring: warp-independent run kernel on the cached run plan
+    bool use_run = fast && c.nnz >= 4096;
+    if (const char *e = getenv("B200GRB_SPMV_RUN")) use_run = fast && c.nnz > 0 && atoi(e) != 0;
+    if (use_run) {
+        GB_TRY(spmv_run_plan(c, err));
+        CU_TRY(cudaMemsetAsync(tval, 0, (size_t)n * zsz, G.stream), err);
+        CU_TRY(cudaMemcpyAsync(tpres, c.pres_tmpl, (size_t)n, cudaMemcpyDeviceToDevice, G.stream), err);
+        RunArgs ra{};
+        ra.col = c.col; ra.aval = aval; ra.uval = uval; ra.headw = c.run_headw; ra.lane_rank = c.run_lane; ra.run_base = c.run_base;
+        ra.nzrow = c.nzrow; ra.rowptr = c.rowptr32; ra.nruns = c.nruns; ra.nnz = c.nnz; ra.tval = tval;
+        GB_TRY(dmalloc(&ra.head_val, (size_t)c.nruns * zsz + 16, err));
+        GB_TRY(dmalloc(&ra.tail_val, (size_t)c.nruns * zsz + 16, err));
+        GB_TRY(dmalloc((void **)&ra.head_has, (size_t)c.nruns + 16, err));
+        GB_TRY(dalloc(&ra.tail_rank, (size_t)c.nruns, err));
+        void *u_perm = nullptr; size_t hot_bytes = 0;
+        const char *hot_env = getenv("B200GRB_SPMV_HOT");
+        if (need_u && hot_env && atoi(hot_env) > 0 && c.nnz >= ((int64_t)1 << 20) && c.ncols >= (1 << 16)) {
+            GB_TRY(spmv_hot_plan(c, err));
+            const size_t xsz = (size_t)tc_size(xt);
+            GB_TRY(dmalloc(&u_perm, (size_t)c.hused * xsz + 16, err));
+            if (c.hused > 0) { permute_u_kernel<<<hgrid(c.hused), 256, 0, G.stream>>>(c.hperm, (const uint8_t *)uval, (uint8_t *)u_perm, (int)xsz, c.hused); GB_LAUNCHED(); }
+            ra.col = c.hcol; ra.uval = u_perm; hot_bytes = (size_t)atoi(hot_env) << 10;
+        }
+        const bool ok = spmv_run_dispatch(xt, add, kmul, ra, hot_bytes, c.hused);
+        dfree(u_perm); dfree(ra.head_val); dfree(ra.tail_val); dfree(ra.head_has); dfree(ra.tail_rank);
+        if (!ok) { dfree(tval); dfree(tpres); dfree(a_cast); dfree(u_cast); return gb_fail(GrB_PANIC, err, "mxv: internal dispatch error"); }
+    } else if (c.nnz == 0) {
         clear_presence_kernel<<<grid_for(n), 256, 0, G.stream>>>(tpres, n); GB_LAUNCHED();
     } else {
         SpmvArgs a{};

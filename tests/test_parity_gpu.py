@@ -252,13 +252,14 @@ def test_rmat_masked_mxm_large_ST1_and_valued_mask():
     assert np.array_equal(Bp, R2.indptr) and np.array_equal(Bj, R2.indices) and np.array_equal(Bx, R2.data.astype(np.int64))
 
 
-@pytest.mark.parametrize("mode", [{}, {"B200GRB_SPMV_ITEMS": "16"}, {"B200GRB_SPMV_HOT": "64"}, {"B200GRB_SPMV_HOT": "32", "B200GRB_HOT_GROUPS": "2"}])
+@pytest.mark.parametrize("mode", [{}, {"B200GRB_SPMV_HOT": "64"}, {"B200GRB_SPMV_RUN": "0"}, {"B200GRB_SPMV_RUN": "0", "B200GRB_SPMV_ITEMS": "16"},
+                                  {"B200GRB_SPMV_RUN": "0", "B200GRB_SPMV_HOT": "32", "B200GRB_HOT_GROUPS": "2"}])
 def test_large_spmv_all_kernel_variants(mode):
-    """Large dense-u SpMV through every kernel variant (one CTA per tile with 8 / 16 entries per thread,
-    persistent hot-column kernel with 4 / 2 groups): exact against the oracle on small-integer data, for
-    specialised and run-time semirings."""
+    """Large dense-u SpMV through every kernel variant (run kernel, run kernel + hot-column table, tile
+    kernel with 8 / 16 entries per thread, persistent hot tile kernel): exact against the oracle on
+    small-integer data, for specialised and run-time semirings."""
     import os
-    old = {k: os.environ.get(k) for k in ("B200GRB_SPMV_ITEMS", "B200GRB_SPMV_HOT", "B200GRB_HOT_GROUPS")}
+    old = {k: os.environ.get(k) for k in ("B200GRB_SPMV_ITEMS", "B200GRB_SPMV_HOT", "B200GRB_HOT_GROUPS", "B200GRB_SPMV_RUN")}
     os.environ.update(mode)
     try:
         _large_spmv_body()

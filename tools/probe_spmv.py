@@ -18,8 +18,11 @@ sp_ = gb.ffi.new("void**"); gb.lib.B200_get_stream(sp_)
 stream = torch.cuda.ExternalStream(int(gb.ffi.cast("uintptr_t", sp_[0])))
 
 def run(label, sr, env):
-    for k in ("B200GRB_SPMV_ITEMS", "B200GRB_SPMV_HOT", "B200GRB_HOT_GROUPS", "B200GRB_SPMV_DEBUG"):
+    keep_run = os.environ.get("B200GRB_SPMV_RUN")
+    for k in ("B200GRB_SPMV_ITEMS", "B200GRB_SPMV_HOT", "B200GRB_HOT_GROUPS", "B200GRB_SPMV_DEBUG", "B200GRB_SPMV_RUN"):
         os.environ.pop(k, None)
+    if keep_run is not None and "B200GRB_SPMV_RUN" not in env:
+        os.environ["B200GRB_SPMV_RUN"] = keep_run
     os.environ.update(env)
     for _ in range(5):
         A.mxv(u, semiring=sr, out=w)
@@ -33,9 +36,14 @@ def run(label, sr, env):
     ms = e0.elapsed_time(e1) / 30
     print(f"{label:44s} {ms*1e3:8.1f} us", flush=True)
 
-for kb in ("1", "4", "8", "16"):
-    run(f"persistent groups=1 table={kb}KB PLUS_TIMES", FP32.PLUS_TIMES, {"B200GRB_SPMV_HOT": kb, "B200GRB_HOT_GROUPS": "1"})
-run("persistent groups=1 table=1KB MIN_PLUS", FP32.MIN_PLUS, {"B200GRB_SPMV_HOT": "1", "B200GRB_HOT_GROUPS": "1"})
+run("run kernel PLUS_TIMES", FP32.PLUS_TIMES, {})
+run("run kernel PLUS_SECOND", FP32.PLUS_SECOND, {})
+run("run kernel PLUS_FIRST (no gather)", FP32.PLUS_FIRST, {})
+run("run kernel PLUS_PAIR (col only)", FP32.PLUS_PAIR, {})
+run("run kernel MIN_PLUS", FP32.MIN_PLUS, {})
+for kb in ("32", "64", "96", "128", "160", "192"):
+    run(f"run kernel + hot table {kb}KB PLUS_TIMES", FP32.PLUS_TIMES, {"B200GRB_SPMV_HOT": kb})
+os.environ["B200GRB_SPMV_RUN"] = "0"
 for items in ("8",):
     env = {"B200GRB_SPMV_ITEMS": items}
     run(f"items={items} PLUS_TIMES  (col + val stream, gather)", FP32.PLUS_TIMES, env)
