@@ -277,7 +277,7 @@ def run_b200(args):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "spmv_tile_kernel<float,float,PLUS,TIMES> (+ fix-up)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "spmv_run_hot_kernel<float,float,PLUS,TIMES> (+ u permute, fix-up)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg_bytes,
                 "kernel_ms": kms, "peak_source": peak_src}
 

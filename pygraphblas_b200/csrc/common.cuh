@@ -70,6 +70,7 @@ struct Csr {
     uint32_t *hperm = nullptr;     // [ncols] new id -> original column
     uint32_t *hcol = nullptr;      // [nnz] relabelled column ids
     int64_t hused = 0;             // columns that occur at least once
+    double hot_cover = 0.0;        // share of the entries whose column is among the 40960 most referenced
     bool valid = false;
 };
 

@@ -495,8 +495,8 @@ __global__ void __launch_bounds__(256) spmv_run_kernel(const RunArgs p) {
     spmv_run_body<XT, ZT, ADD, MUL, false>(p, run, threadIdx.x & 31, nullptr, 0u);
 }
 
-template <typename XT, typename ZT, int ADD, int MUL>
-__global__ void __launch_bounds__(1024, 1) spmv_run_hot_kernel(const RunArgs p, const uint32_t hot_n) {
+template <typename XT, typename ZT, int ADD, int MUL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) spmv_run_hot_kernel(const RunArgs p, const uint32_t hot_n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     XT *s_hot = reinterpret_cast<XT *>(smem_raw);
     const XT *uval = static_cast<const XT *>(p.uval);
@@ -598,11 +598,20 @@ static GrB_Info spmv_run_plan(Csr &c, std::string *err) {
 template <typename XT, typename ZT, int ADD, int MUL>
 static void spmv_run_launch(const RunArgs &a, size_t hot_bytes, int64_t hused) {
     if (hot_bytes) {
-        auto kernel = spmv_run_hot_kernel<XT, ZT, ADD, MUL>;
+        // two shapes: one 1024-thread CTA per SM with a table of up to ~200 KB, or two 768-thread CTAs
+        // per SM (<= 42 registers) with a table of up to ~100 KB each
+        const bool two = hot_bytes <= ((size_t)104 << 10) && getenv("B200GRB_HOT_ONE") == nullptr;
         const uint32_t hot_n = (uint32_t)std::min<int64_t>(hused, (int64_t)(hot_bytes / sizeof(XT)));
         const size_t smem = (size_t)hot_n * sizeof(XT);
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kernel<<<G.num_sms, 1024, smem, G.stream>>>(a, hot_n); GB_LAUNCHED();
+        if (two) {
+            auto kernel = spmv_run_hot_kernel<XT, ZT, ADD, MUL, 768, 2>;
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kernel<<<G.num_sms * 2, 768, smem, G.stream>>>(a, hot_n); GB_LAUNCHED();
+        } else {
+            auto kernel = spmv_run_hot_kernel<XT, ZT, ADD, MUL, 1024, 1>;
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kernel<<<G.num_sms, 1024, smem, G.stream>>>(a, hot_n); GB_LAUNCHED();
+        }
     } else {
         spmv_run_kernel<XT, ZT, ADD, MUL><<<(unsigned)ceil_div(a.nruns, 8), 256, 0, G.stream>>>(a); GB_LAUNCHED();
     }
@@ -703,6 +712,12 @@ __global__ void hot_invert_kernel(const uint32_t *perm, const uint32_t *deg_sort
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(used, c);
 }
+__global__ void hot_cover_kernel(const uint32_t *deg_sorted, int64_t k, unsigned long long *sum) {
+    unsigned long long c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (int64_t)gridDim.x * blockDim.x) c += deg_sorted[i];
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(sum, c);
+}
 __global__ void hot_relabel_kernel(const uint32_t *col, const uint32_t *inv, int64_t nnz, uint32_t *out) {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) out[k] = inv[col[k]];
 }
@@ -713,11 +728,11 @@ static GrB_Info spmv_hot_plan(Csr &c, std::string *err) {
     const int64_t n = c.ncols;
     uint32_t *deg = nullptr, *deg_sorted = nullptr, *ids = nullptr, *inv = nullptr; unsigned long long *used = nullptr;
     GB_TRY(dalloc(&deg, (size_t)n, err)); GB_TRY(dalloc(&deg_sorted, (size_t)n, err)); GB_TRY(dalloc(&ids, (size_t)n, err));
-    GB_TRY(dalloc(&inv, (size_t)n, err)); GB_TRY(dalloc(&used, 1, err));
+    GB_TRY(dalloc(&inv, (size_t)n, err)); GB_TRY(dalloc(&used, 2, err));
     GB_TRY(dalloc(&c.hperm, (size_t)n, err));
     GB_TRY(dalloc(&c.hcol, (size_t)c.nnz, err));
     CU_TRY(cudaMemsetAsync(deg, 0, (size_t)n * 4, G.stream), err);
-    CU_TRY(cudaMemsetAsync(used, 0, 8, G.stream), err);
+    CU_TRY(cudaMemsetAsync(used, 0, 16, G.stream), err);
     hot_count_kernel<<<hgrid(c.nnz), 256, 0, G.stream>>>(c.col, c.nnz, deg); GB_LAUNCHED();
     hot_iota_kernel<<<hgrid(n), 256, 0, G.stream>>>(ids, n); GB_LAUNCHED();
     size_t tmp_bytes = 0;     // stable sort: equal degrees keep ascending column order (deterministic plan)
@@ -727,10 +742,13 @@ static GrB_Info spmv_hot_plan(Csr &c, std::string *err) {
     G.launches += 8;
     hot_invert_kernel<<<hgrid(n), 256, 0, G.stream>>>(c.hperm, deg_sorted, n, inv, used); GB_LAUNCHED();
     hot_relabel_kernel<<<hgrid(c.nnz), 256, 0, G.stream>>>(c.col, inv, c.nnz, c.hcol); GB_LAUNCHED();
-    unsigned long long h = 0;
-    CU_TRY(cudaMemcpyAsync(&h, used, 8, cudaMemcpyDeviceToHost, G.stream), err);
+    const int64_t topk = std::min<int64_t>(n, 40960);
+    hot_cover_kernel<<<hgrid(topk), 256, 0, G.stream>>>(deg_sorted, topk, used + 1); GB_LAUNCHED();
+    unsigned long long h[2] = {0, 0};
+    CU_TRY(cudaMemcpyAsync(h, used, 16, cudaMemcpyDeviceToHost, G.stream), err);
     CU_TRY(cudaStreamSynchronize(G.stream), err);
-    c.hused = (int64_t)h;
+    c.hused = (int64_t)h[0];
+    c.hot_cover = c.nnz ? (double)h[1] / (double)c.nnz : 0.0;
     dfree(tmp); dfree(deg); dfree(deg_sorted); dfree(ids); dfree(inv); dfree(used);
     return GrB_SUCCESS;
 }
@@ -930,13 +948,19 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
         GB_TRY(dmalloc((void **)&ra.head_has, (size_t)c.nruns + 16, err));
         GB_TRY(dalloc(&ra.tail_rank, (size_t)c.nruns, err));
         void *u_perm = nullptr; size_t hot_bytes = 0;
+        // hot-column table: on by default for large matrices whose gathers are concentrated (R-MAT-like);
+        // B200GRB_SPMV_HOT=0 disables it, =<KB> forces a table size
         const char *hot_env = getenv("B200GRB_SPMV_HOT");
-        if (need_u && hot_env && atoi(hot_env) > 0 && c.nnz >= ((int64_t)1 << 20) && c.ncols >= (1 << 16)) {
+        int hot_kb = hot_env ? atoi(hot_env) : 160;
+        if (need_u && hot_kb > 0 && c.nnz >= ((int64_t)1 << 20) && c.ncols >= (1 << 16)) {
             GB_TRY(spmv_hot_plan(c, err));
+            if (!hot_env && c.hot_cover < 0.25) hot_kb = 0;
+        } else hot_kb = 0;
+        if (hot_kb > 0) {
             const size_t xsz = (size_t)tc_size(xt);
             GB_TRY(dmalloc(&u_perm, (size_t)c.hused * xsz + 16, err));
             if (c.hused > 0) { permute_u_kernel<<<hgrid(c.hused), 256, 0, G.stream>>>(c.hperm, (const uint8_t *)uval, (uint8_t *)u_perm, (int)xsz, c.hused); GB_LAUNCHED(); }
-            ra.col = c.hcol; ra.uval = u_perm; hot_bytes = (size_t)atoi(hot_env) << 10;
+            ra.col = c.hcol; ra.uval = u_perm; hot_bytes = (size_t)hot_kb << 10;
         }
         const bool ok = spmv_run_dispatch(xt, add, kmul, ra, hot_bytes, c.hused);
         dfree(u_perm); dfree(ra.head_val); dfree(ra.tail_val); dfree(ra.head_has); dfree(ra.tail_rank);

@@ -41,14 +41,6 @@ run("run kernel PLUS_SECOND", FP32.PLUS_SECOND, {})
 run("run kernel PLUS_FIRST (no gather)", FP32.PLUS_FIRST, {})
 run("run kernel PLUS_PAIR (col only)", FP32.PLUS_PAIR, {})
 run("run kernel MIN_PLUS", FP32.MIN_PLUS, {})
-for kb in ("32", "64", "96", "128", "160", "192"):
+for kb in ("32", "64", "80", "96", "104", "128", "160"):
     run(f"run kernel + hot table {kb}KB PLUS_TIMES", FP32.PLUS_TIMES, {"B200GRB_SPMV_HOT": kb})
-os.environ["B200GRB_SPMV_RUN"] = "0"
-for items in ("8",):
-    env = {"B200GRB_SPMV_ITEMS": items}
-    run(f"items={items} PLUS_TIMES  (col + val stream, gather)", FP32.PLUS_TIMES, env)
-    run(f"items={items} PLUS_SECOND (col stream, gather)", FP32.PLUS_SECOND, env)
-    run(f"items={items} PLUS_FIRST  (col + val stream, no gather)", FP32.PLUS_FIRST, env)
-    run(f"items={items} PLUS_PAIR   (col stream only)", FP32.PLUS_PAIR, env)
-    run(f"items={items} MIN_PLUS", FP32.MIN_PLUS, env)
 run("run-time operators: PLUS_MINUS", FP32.PLUS_MINUS, {})
