@@ -81,7 +81,9 @@ template <typename ZT> __device__ __forceinline__ void atomic_combine(typename S
     }
 }
 
-__device__ __forceinline__ uint32_t hash_col(uint32_t c, uint32_t mask) { return (c * 2654435761u) & mask; }
+// multiplicative (Fibonacci) hashing: the HIGH bits of c * 2^32/phi index a table of 2^k slots (shift = 32 - k);
+// the low bits would only permute the low bits of c and cluster structured column ids
+__device__ __forceinline__ uint32_t hash_col(uint32_t c, int shift) { return (c * 2654435761u) >> shift; }
 
 struct GemmArgs {
     const uint32_t *a_ptr, *a_col; const void *a_val;
@@ -166,6 +168,7 @@ __global__ void __launch_bounds__(256) hash_symbolic_kernel(const GemmArgs p) {
     const int64_t idx = (int64_t)blockIdx.x * groups + gid;
     const bool active = idx < p.nbin;
     const uint32_t tmask = (uint32_t)p.table - 1;
+    const int hshift = __clz(p.table) + 1;                            // 32 - log2(table)
     for (int s = tid; s < p.table; s += gsize) keys[s] = EMPTY_KEY;
     if (tid == 0) s_count[gid] = 0;
     group_sync<WARP>();
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(256) hash_symbolic_kernel(const GemmArgs p) {
                 const uint32_t k = p.a_col[pa];
                 for (uint32_t pb = p.b_ptr[k]; pb < p.b_ptr[k + 1]; ++pb) {
                     const uint32_t j = __ldg(p.b_col + pb);
-                    uint32_t s = hash_col(j, tmask);
+                    uint32_t s = hash_col(j, hshift);
                     while (true) {
                         const uint32_t seen = atomicCAS(&keys[s], EMPTY_KEY, j);
                         if (seen == EMPTY_KEY) { ++mine; break; }
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(256) hash_symbolic_kernel(const GemmArgs p) {
                 const uint32_t k = p.a_col[pa];
                 for (uint32_t pb = p.b_ptr[k] + lane; pb < p.b_ptr[k + 1]; pb += 32) {
                     const uint32_t j = __ldg(p.b_col + pb);
-                    uint32_t s = hash_col(j, tmask);
+                    uint32_t s = hash_col(j, hshift);
                     while (true) {
                         const uint32_t seen = atomicCAS(&keys[s], EMPTY_KEY, j);
                         if (seen == EMPTY_KEY) { ++mine; break; }
@@ -227,6 +230,7 @@ __global__ void __launch_bounds__(256) hash_numeric_kernel(const GemmArgs p) {
     const int64_t idx = (int64_t)blockIdx.x * groups + gid;
     const bool active = idx < p.nbin;
     const uint32_t tmask = (uint32_t)p.table - 1;
+    const int hshift = __clz(p.table) + 1;                            // 32 - log2(table)
     const W ident = pack_slot<ZT>(monoid_identity<ZT>(add));
     for (int s = tid; s < p.table; s += gsize) { packed[s] = ((unsigned long long)EMPTY_KEY << 32) | (unsigned)s; vals[s] = ident; }
     group_sync<WARP>();
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(256) hash_numeric_kernel(const GemmArgs p) {
         row = p.rows[idx];
         const uint32_t as = p.a_ptr[row], ae = p.a_ptr[row + 1];
         auto insert = [&](uint32_t j, ZT prod) {
-            uint32_t s = hash_col(j, tmask);
+            uint32_t s = hash_col(j, hshift);
             while (true) {
                 uint32_t *kp = reinterpret_cast<uint32_t *>(&packed[s]) + 1;   // high word = key
                 const uint32_t seen = atomicCAS(kp, EMPTY_KEY, j);
@@ -473,6 +477,7 @@ __global__ void __launch_bounds__(256) masked_hash_kernel(const MaskedArgs ma) {
     const int64_t idx = (int64_t)blockIdx.x * groups + gid;
     const bool active = WARP ? idx < p.nbin : idx < ma.nchunks;
     const uint32_t tmask = (uint32_t)p.table - 1;
+    const int hshift = __clz(p.table) + 1;                            // 32 - log2(table)
     const W ident = pack_slot<ZT>(monoid_identity<ZT>(add));
     int64_t row = 0; uint32_t ms = 0, me = 0, nparts = 1, part = 0;
     if (active) {
@@ -491,7 +496,7 @@ __global__ void __launch_bounds__(256) masked_hash_kernel(const MaskedArgs ma) {
             if (!p.m_struct) on = sc_cast(sc_load(p.m_tc, p.m_val, q), p.m_tc, TC_BOOL).u != 0;
             if (!on) continue;
             const uint32_t j = p.m_col[q];
-            uint32_t s = hash_col(j, tmask);
+            uint32_t s = hash_col(j, hshift);
             while (atomicCAS(&keys[s], EMPTY_KEY, j) != EMPTY_KEY) s = (s + 1) & tmask;   // mask columns are unique
             slot[s] = q - ms;
         }
@@ -500,7 +505,7 @@ __global__ void __launch_bounds__(256) masked_hash_kernel(const MaskedArgs ma) {
     if (active) {
         const XT *bval = static_cast<const XT *>(p.b_val);
         auto hit = [&](uint32_t j, XT av, uint32_t pb) {
-            uint32_t s = hash_col(j, tmask);
+            uint32_t s = hash_col(j, hshift);
             while (true) {
                 const uint32_t kk = keys[s];
                 if (kk == j) {
