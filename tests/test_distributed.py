@@ -45,6 +45,57 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _worker_scattered(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    from pygraphblas_b200.distributed import local_block_scattered, to_scattered
+    from pygraphblas_b200.generators import rmat_csr
+    from oracle import oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, indptr, indices = rmat_csr(11, 8, seed=3)
+    rng = np.random.default_rng(0)
+    vals = (rng.integers(1, 9, len(indices)) / 4.0).astype(np.float32)
+    u = (rng.integers(0, 9, n) / 4.0).astype(np.float32)
+    newid, lb, lptr, lidx, lval = local_block_scattered(indptr, indices, vals, world, rank)
+    full = torch.from_numpy(to_scattered(u, newid, world * lb))
+    L = orc.lib()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for _ in range(3):
+        w = np.zeros(lb, np.float32); pres = np.zeros(lb, np.uint8)
+        uu = full.numpy().copy()
+        L.fast_spmv_plus_times_f32(ctypes.c_int64(lb), p(lptr), p(np.ascontiguousarray(lidx)), p(np.ascontiguousarray(lval)), p(uu), p(w), p(pres))
+        dist.all_gather_into_tensor(full, torch.from_numpy(w))        # the call bench.py issues with NCCL
+    if rank == 0:
+        np.save(out, full.numpy()[newid])                             # back to the original vertex order
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_scattered_equal_blocks_world2(tmp_path):
+    """bench.py's multi-GPU layout: pseudo-random vertex relabelling -> equal-length, equal-work blocks ->
+    one all_gather_into_tensor per step."""
+    import torch.multiprocessing as mp
+    from pygraphblas_b200.generators import rmat_csr
+    from pygraphblas_b200.distributed import local_block_scattered
+    import scipy.sparse as sp
+    out = str(tmp_path / "w2.npy")
+    mp.spawn(_worker_scattered, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    n, indptr, indices = rmat_csr(11, 8, seed=3)
+    rng = np.random.default_rng(0)
+    vals = (rng.integers(1, 9, len(indices)) / 4.0).astype(np.float32)
+    u = (rng.integers(0, 9, n) / 4.0).astype(np.float32)
+    A = sp.csr_matrix((vals.astype(np.float64), indices, indptr), shape=(n, n))
+    ref = u.astype(np.float64)
+    for _ in range(3):
+        ref = A @ ref
+    assert np.allclose(got, ref, rtol=1e-5)
+    work = [len(local_block_scattered(indptr, indices, vals, 8, r)[3]) for r in range(8)]
+    assert max(work) <= 1.35 * (sum(work) / 8)
+
+
 def test_row_block_allgather_world2(tmp_path):
     import torch.multiprocessing as mp
     from pygraphblas_b200.generators import rmat_csr, row_block_bounds
