@@ -62,7 +62,9 @@ struct Csr {
     // run plan (spmv.cu, dense-u kernel): entries cut into warp-sized runs of 256
     uint32_t *run_headw = nullptr;   // [ceil(nnz/32)] bit q = entry q starts a row
     uint16_t *run_lane = nullptr;    // [nruns*32] row starts inside the run before the lane's first entry
-    uint32_t *run_base = nullptr;    // [nruns] row starts before the run (= rank of its first row start)
+    uint32_t *run_base = nullptr;    // [nruns+1] row starts before the run (= rank of its first row start)
+    int32_t *run_tail_row = nullptr; // [nruns] row still open at the end of the run (its last row start), or -1
+    uint32_t *run_tail_last = nullptr; // [nruns] last run that row reaches
     uint32_t *nzrow = nullptr;       // [nnzrows] ids of the non-empty rows, ascending
     uint8_t *pres_tmpl = nullptr;    // [nrows] 1 where the row is non-empty
     int64_t nruns = 0, nnzrows = 0;

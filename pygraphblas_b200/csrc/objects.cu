@@ -129,7 +129,7 @@ GrB_Info dmalloc(void **p, size_t bytes, std::string *err) {
 void dfree(void *p) { if (p && G.have_device) cudaFreeAsync(p, G.stream); }
 
 void csr_free(Csr &c) {
-    dfree(c.rowptr); dfree(c.rowptr32); dfree(c.col); dfree(c.val); dfree(c.tile_row); dfree(c.hperm); dfree(c.hcol); dfree(c.run_headw); dfree(c.run_lane); dfree(c.run_base); dfree(c.nzrow); dfree(c.pres_tmpl);
+    dfree(c.rowptr); dfree(c.rowptr32); dfree(c.col); dfree(c.val); dfree(c.tile_row); dfree(c.hperm); dfree(c.hcol); dfree(c.run_headw); dfree(c.run_lane); dfree(c.run_base); dfree(c.run_tail_row); dfree(c.run_tail_last); dfree(c.nzrow); dfree(c.pres_tmpl);
     c = Csr();
 }
 

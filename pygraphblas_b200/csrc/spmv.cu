@@ -390,9 +390,10 @@ static constexpr int RUN = 256;
 struct RunArgs {
     const uint32_t *col; const void *aval; const void *uval;
     const uint32_t *headw; const uint16_t *lane_rank; const uint32_t *run_base; const uint32_t *nzrow; const uint32_t *rowptr;
+    const int32_t *tail_row; const uint32_t *tail_last;       // structural: which row is open at a run's end, how far it reaches
     int64_t nruns; int64_t nnz;
     void *tval;
-    void *head_val; uint8_t *head_has; void *tail_val; int32_t *tail_rank;
+    void *head_val; void *tail_val;                            // per run: partial of the row it starts inside / of the row open at its end
 };
 
 template <typename XT, typename ZT, int ADD, int MUL, bool HOT>
@@ -473,19 +474,13 @@ __device__ __forceinline__ void spmv_run_body(const RunArgs &p, const int64_t ru
     if (lane == 31) { nxt.has = 0; nxt_stop = 0; }
 
     // the lane holding the last row start of the run owns the row that is still open at the run's end
-    const bool open_tail = seen && !nxt_stop;
+    // (which row that is, and where it ends, is structural: run_tail_row / run_tail_last of the plan)
     if (seen) {
         const Part<ZT> total = part_join<ZT>(ADD, acc, nxt);
         if (nxt_stop) tval[__ldg(p.nzrow + cur)] = total.v;
-        else { static_cast<ZT *>(p.tail_val)[run] = total.v; p.tail_rank[run] = (int32_t)cur; }
+        else static_cast<ZT *>(p.tail_val)[run] = total.v;
     }
-    const unsigned any_tail = __ballot_sync(0xffffffffu, open_tail);
-    if (lane == 0) {
-        const bool inside = !(hb & 1u) && nvalid > 0;                       // the run starts inside a row of an earlier run
-        if (inside) static_cast<ZT *>(p.head_val)[run] = x.v;
-        p.head_has[run] = inside ? (uint8_t)x.has : (uint8_t)0;
-        if (!any_tail) p.tail_rank[run] = -1;
-    }
+    if (lane == 0 && !(hb & 1u) && nvalid > 0) static_cast<ZT *>(p.head_val)[run] = x.v;   // the run starts inside a row of an earlier run
 }
 
 template <typename XT, typename ZT, int ADD, int MUL>
@@ -507,21 +502,18 @@ __global__ void __launch_bounds__(THREADS, MINB) spmv_run_hot_kernel(const RunAr
         spmv_run_body<XT, ZT, ADD, MUL, true>(p, run, threadIdx.x & 31, s_hot, hot_n);
 }
 
-// rows that continue past their run: tail partial (+) head partials of the following runs, 8 lanes per open row
+// rows that continue past their run: tail partial (+) head partials of the following runs, 8 lanes per open row.
+// Every run after `run` up to tail_last starts inside that row, so its head partial exists.
 template <typename ZT, int ADD>
 __global__ void __launch_bounds__(256) spmv_run_fixup_kernel(const RunArgs p) {
     const int sub = threadIdx.x & 7;
     const int64_t run = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const bool active = run < p.nruns;
-    int32_t rk = active ? p.tail_rank[run] : -1;
-    // all 8 lanes of a group take the same branch; shuffles below use the full mask with width 8
+    const int32_t r = run < p.nruns ? __ldg(p.tail_row + run) : -1;
     Part<ZT> acc{(ZT)0, 0};
-    uint32_t r = 0;
-    if (rk >= 0) {
-        r = p.nzrow[rk];
-        const int64_t last_run = ((int64_t)p.rowptr[r + 1] - 1) / RUN;
+    if (r >= 0) {
+        const int64_t last_run = __ldg(p.tail_last + run);
         if (sub == 0) { acc.v = static_cast<const ZT *>(p.tail_val)[run]; acc.has = 1; }
-        for (int64_t t = run + 1 + sub; t <= last_run; t += 8) if (p.head_has[t]) {
+        for (int64_t t = run + 1 + sub; t <= last_run; t += 8) {
             const Part<ZT> y{static_cast<const ZT *>(p.head_val)[t], 1};
             acc = part_join<ZT>(ADD, acc, y);
         }
@@ -531,7 +523,7 @@ __global__ void __launch_bounds__(256) spmv_run_fixup_kernel(const RunArgs p) {
         Part<ZT> y; y.v = shfl_xor_t<ZT>(acc.v, o); y.has = __shfl_xor_sync(0xffffffffu, acc.has, o);
         acc = part_join<ZT>(ADD, acc, y);
     }
-    if (rk >= 0 && sub == 0) static_cast<ZT *>(p.tval)[r] = acc.v;
+    if (r >= 0 && sub == 0) static_cast<ZT *>(p.tval)[r] = acc.v;
 }
 
 // ---- run plan (cached per CSR)
@@ -560,7 +552,21 @@ __global__ void plan_runs_kernel(const uint32_t *headw, int64_t nruns, int64_t n
     if (lane == 31) run_cnt[run] = inc;
 }
 __global__ void plan_base_kernel(const int64_t *scan, int64_t nruns, uint32_t *run_base) {
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nruns; k += (int64_t)gridDim.x * blockDim.x) run_base[k] = (uint32_t)scan[k];
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k <= nruns; k += (int64_t)gridDim.x * blockDim.x) run_base[k] = (uint32_t)scan[k];
+}
+// the row that starts last inside a run always holds the run's last entry: it is the run's "open" row
+// (possibly ending exactly at the run's end), completed by the fix-up kernel
+__global__ void plan_tails_kernel(const uint32_t *run_base, const uint32_t *nzrow, const uint32_t *rowptr, int64_t nruns,
+                                  int32_t *tail_row, uint32_t *tail_last) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nruns; k += (int64_t)gridDim.x * blockDim.x) {
+        int32_t tr = -1; uint32_t tl = 0;
+        if (run_base[k + 1] > run_base[k]) {
+            const uint32_t r = nzrow[run_base[k + 1] - 1];
+            const uint32_t re = rowptr[r + 1];
+            tr = (int32_t)r; tl = (re - 1) / RUN;
+        }
+        tail_row[k] = tr; tail_last[k] = tl;
+    }
 }
 static inline int rgrid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), (int64_t)G.num_sms * 16)); }
 
@@ -575,7 +581,9 @@ static GrB_Info spmv_run_plan(Csr &c, std::string *err) {
     GB_TRY(dalloc(&c.pres_tmpl, (size_t)c.nrows, err));
     GB_TRY(dalloc(&c.run_headw, (size_t)nwords + 8, err));
     GB_TRY(dalloc(&c.run_lane, (size_t)c.nruns * 32, err));
-    GB_TRY(dalloc(&c.run_base, (size_t)c.nruns, err));
+    GB_TRY(dalloc(&c.run_base, (size_t)c.nruns + 1, err));
+    GB_TRY(dalloc(&c.run_tail_row, (size_t)c.nruns, err));
+    GB_TRY(dalloc(&c.run_tail_last, (size_t)c.nruns, err));
     CU_TRY(cudaMemsetAsync(c.run_headw, 0, ((size_t)nwords + 8) * 4, G.stream), err);
     CU_TRY(cudaMemsetAsync(flag + c.nrows, 0, 8, G.stream), err);
     plan_nonempty_kernel<<<rgrid(c.nrows), 256, 0, G.stream>>>(c.rowptr32, c.nrows, flag, c.pres_tmpl); GB_LAUNCHED();
@@ -589,7 +597,8 @@ static GrB_Info spmv_run_plan(Csr &c, std::string *err) {
     CU_TRY(cudaMemsetAsync(cnt + c.nruns, 0, 8, G.stream), err);
     plan_runs_kernel<<<(unsigned)ceil_div(c.nruns * 32, 256), 256, 0, G.stream>>>(c.run_headw, c.nruns, nwords, c.run_lane, cnt); GB_LAUNCHED();
     GB_TRY(dev_exclusive_scan(cnt, c.nruns + 1, err));
-    plan_base_kernel<<<rgrid(c.nruns), 256, 0, G.stream>>>(cnt, c.nruns, c.run_base); GB_LAUNCHED();
+    plan_base_kernel<<<rgrid(c.nruns + 1), 256, 0, G.stream>>>(cnt, c.nruns, c.run_base); GB_LAUNCHED();
+    plan_tails_kernel<<<rgrid(c.nruns), 256, 0, G.stream>>>(c.run_base, c.nzrow, c.rowptr32, c.nruns, c.run_tail_row, c.run_tail_last); GB_LAUNCHED();
     dfree(flag); dfree(cnt);
     CU_TRY(cudaGetLastError(), err);
     return GrB_SUCCESS;
@@ -943,10 +952,9 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
         RunArgs ra{};
         ra.col = c.col; ra.aval = aval; ra.uval = uval; ra.headw = c.run_headw; ra.lane_rank = c.run_lane; ra.run_base = c.run_base;
         ra.nzrow = c.nzrow; ra.rowptr = c.rowptr32; ra.nruns = c.nruns; ra.nnz = c.nnz; ra.tval = tval;
+        ra.tail_row = c.run_tail_row; ra.tail_last = c.run_tail_last;
         GB_TRY(dmalloc(&ra.head_val, (size_t)c.nruns * zsz + 16, err));
         GB_TRY(dmalloc(&ra.tail_val, (size_t)c.nruns * zsz + 16, err));
-        GB_TRY(dmalloc((void **)&ra.head_has, (size_t)c.nruns + 16, err));
-        GB_TRY(dalloc(&ra.tail_rank, (size_t)c.nruns, err));
         void *u_perm = nullptr; size_t hot_bytes = 0;
         // hot-column table: on by default for large matrices whose gathers are concentrated (R-MAT-like);
         // B200GRB_SPMV_HOT=0 disables it, =<KB> forces a table size
@@ -963,7 +971,7 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
             ra.col = c.hcol; ra.uval = u_perm; hot_bytes = (size_t)hot_kb << 10;
         }
         const bool ok = spmv_run_dispatch(xt, add, kmul, ra, hot_bytes, c.hused);
-        dfree(u_perm); dfree(ra.head_val); dfree(ra.tail_val); dfree(ra.head_has); dfree(ra.tail_rank);
+        dfree(u_perm); dfree(ra.head_val); dfree(ra.tail_val);
         if (!ok) { dfree(tval); dfree(tpres); dfree(a_cast); dfree(u_cast); return gb_fail(GrB_PANIC, err, "mxv: internal dispatch error"); }
     } else if (c.nnz == 0) {
         clear_presence_kernel<<<grid_for(n), 256, 0, G.stream>>>(tpres, n); GB_LAUNCHED();
