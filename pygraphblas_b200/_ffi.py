@@ -24,10 +24,14 @@ def header_cdef():
     text = read("b200grb.h")
     text = text.replace('#include "b200grb_ops.h"', read("b200grb_ops.h"))
     text = text.replace('#include "b200grb_typed.h"', read("b200grb_typed.h"))
+    text = text.replace('#include "b200grb_compat.h"', read("b200grb_compat.h"))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     out = []
     for line in text.splitlines():
         s = line.strip()
+        if s.startswith("#define ") and len(s.split()) == 3 and re.fullmatch(r"-?\d+", s.split()[2]):
+            out.append(line)                    # integer constants (GxB_INDEX_MAX, ...) are part of the ABI
+            continue
         if s.startswith("#") or s.startswith('extern "C"') or s == "}":
             continue
         out.append(line)
@@ -43,6 +47,7 @@ def declared_symbols():
             names.add(n.strip().lstrip("*"))
     # enum constants and typedef names are not symbols
     enums = set(re.findall(r"\b((?:GrB|GxB)_[A-Za-z0-9_]+)\s*=\s*-?\d+", cdef))
+    enums |= set(re.findall(r"#define\s+(\w+)", cdef))
     return sorted(n for n in names if n not in enums)
 
 

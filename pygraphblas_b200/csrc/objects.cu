@@ -520,6 +520,7 @@ extern "C" GrB_Info GrB_Matrix_new(GrB_Matrix *A, GrB_Type type, GrB_Index nrows
     if (!A) return gb_fail(GrB_NULL_POINTER, nullptr, "GrB_Matrix_new: NULL handle");
     *A = nullptr;
     if (!valid_type(type)) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "GrB_Matrix_new: bad type");
+    if (type->code >= TC_COUNT) return gb_fail(GrB_DOMAIN_MISMATCH, nullptr, "GrB_Matrix_new: complex and user-defined types are out of scope");
     if (nrows == 0 || ncols == 0 || nrows > ((uint64_t)1 << 60) || ncols > ((uint64_t)1 << 60))
         return gb_fail(GrB_INVALID_VALUE, nullptr, "GrB_Matrix_new: dimensions must be in 1..2^60");
     GB_Matrix_opaque *m = new GB_Matrix_opaque();
@@ -603,8 +604,8 @@ extern "C" GrB_Info GrB_Matrix_wait(GrB_Matrix *A) {
 }
 extern "C" GrB_Info GrB_Matrix_error(const char **error, const GrB_Matrix A) {
     if (!error) return gb_fail(GrB_NULL_POINTER, nullptr, "GrB_Matrix_error: NULL");
-    if (!gb_valid_matrix(A)) { *error = tl_error.c_str(); return GrB_SUCCESS; }
-    if (A->err.empty()) A->err = tl_error;
+    // the reference asks right after a failing call (matrix.py:43-51): report the latest error of this thread
+    if (!gb_valid_matrix(A) || !tl_error.empty()) { *error = tl_error.c_str(); return GrB_SUCCESS; }
     *error = A->err.c_str(); return GrB_SUCCESS;
 }
 
@@ -716,6 +717,7 @@ extern "C" GrB_Info GrB_Vector_new(GrB_Vector *v, GrB_Type type, GrB_Index n) {
     if (!v) return gb_fail(GrB_NULL_POINTER, nullptr, "GrB_Vector_new: NULL handle");
     *v = nullptr;
     if (!valid_type(type)) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "GrB_Vector_new: bad type");
+    if (type->code >= TC_COUNT) return gb_fail(GrB_DOMAIN_MISMATCH, nullptr, "GrB_Vector_new: complex and user-defined types are out of scope");
     if (n == 0 || n > ((uint64_t)1 << 60)) return gb_fail(GrB_INVALID_VALUE, nullptr, "GrB_Vector_new: size must be in 1..2^60");
     GB_Vector_opaque *o = new GB_Vector_opaque();
     o->magic = GB_MAGIC; o->type = type; o->n = n; o->host_valid = true;
@@ -781,8 +783,7 @@ extern "C" GrB_Info GrB_Vector_wait(GrB_Vector *v) {
 }
 extern "C" GrB_Info GrB_Vector_error(const char **error, const GrB_Vector v) {
     if (!error) return gb_fail(GrB_NULL_POINTER, nullptr, "GrB_Vector_error: NULL");
-    if (!gb_valid_vector(v)) { *error = tl_error.c_str(); return GrB_SUCCESS; }
-    if (v->err.empty()) v->err = tl_error;
+    if (!gb_valid_vector(v) || !tl_error.empty()) { *error = tl_error.c_str(); return GrB_SUCCESS; }
     *error = v->err.c_str(); return GrB_SUCCESS;
 }
 static GrB_Info vector_host_writable(GrB_Vector v) {

@@ -1,0 +1,64 @@
+"""The drop-in boundary, exercised with the UNMODIFIED reference package (CPU container only: the
+reference tree does not travel to the GPU box).  `suitesparse_graphblas/` at the repository root is the
+binding stub of INTEGRATION.md; with it ahead on PYTHONPATH, /root/reference/pygraphblas imports and runs
+on libb200grb.so.  Without a GPU the three hot calls must refuse with Panic ("no CPU fallback") -- never
+compute on the host -- while the handle plumbing around them works."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pygraphblas")), reason="reference tree not present")
+
+
+def _run(code):
+    env = dict(os.environ, PYTHONPATH=f"{ROOT}:{REF}")
+    return subprocess.run([sys.executable, "-c", textwrap.dedent(code)], capture_output=True, text=True, env=env, cwd="/tmp", timeout=600)
+
+
+def test_unmodified_reference_imports_and_plumbing_works():
+    r = _run("""
+        import pygraphblas as gb
+        from pygraphblas import Matrix, Vector, Scalar, INT64, BOOL, FP32, descriptor, lib
+        assert gb.__file__.startswith("/root/reference/"), gb.__file__
+        assert lib.GxB_IMPLEMENTATION_MAJOR == 5                    # base.py:37-46 version constants
+        m = Matrix.from_lists([0, 1, 2], [1, 2, 0], [1, 2, 3])       # tests/test_matrix.py:250
+        assert (m.nrows, m.ncols, m.nvals) == (3, 3, 3) and m.type is INT64
+        assert m.to_lists() == [[0, 1, 2], [1, 2, 0], [1, 2, 3]]
+        assert m.iseq(m.dup()) and not m.iseq(Matrix.from_lists([0, 1, 2], [1, 2, 0], [2, 3, 4]))
+        assert m.reduce_int() == 6
+        v = Vector.from_lists([0, 1, 2], [2, 3, 4])
+        assert v.iseq(v.dup()) and v.to_lists() == [[0, 1, 2], [2, 3, 4]]
+        assert INT64.PLUS_TIMES.ztype is INT64 and INT64.min_plus is INT64.MIN_PLUS and BOOL.LOR_LAND.ztype is BOOL
+        assert descriptor.T1 in descriptor.CT1 and descriptor.CT1 == (descriptor.C & descriptor.T1)   # tests/test_descriptor.py:6-10
+        assert Scalar.from_value(3)[0] == 3
+        assert Matrix.sparse(INT64).nrows == 1 << 60                   # matrix.py:167-170
+        print("HAVE_DEVICE", lib.B200_have_device())
+        for call in (lambda: m.mxv(v), lambda: v.vxm(m), lambda: m.mxm(m), lambda: m @ m):
+            try:
+                out = call()
+                assert lib.B200_have_device()
+            except gb.base.Panic as e:
+                assert not lib.B200_have_device() and b"no CPU fallback" in e.args[0]
+        print("OK")
+    """)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_reference_own_tests_run_against_the_library():
+    """Run the reference's own unit tests.  Those that only need handle plumbing must pass; the hot-path
+    ones (test_mxm, test_mxv, test_vxm, test_RC, test_RCT0, ...) may fail ONLY with the no-GPU Panic."""
+    env = dict(os.environ, PYTHONPATH=f"{ROOT}:{REF}")
+    files = [f"{REF}/tests/test_{n}.py" for n in ("matrix", "vector", "descriptor", "scalar", "types", "base")]
+    r = subprocess.run([sys.executable, "-m", "pytest", "-c", "/dev/null", "--rootdir", "/tmp", "-q", "-p", "no:cacheprovider"] + files,
+                       capture_output=True, text=True, env=env, cwd="/tmp", timeout=900)
+    out = r.stdout
+    passed = int(__import__("re").search(r"(\d+) passed", out).group(1)) if " passed" in out else 0
+    assert passed >= 40, out[-3000:]          # 49 of the reference's 121 tests need nothing beyond the hot path's plumbing
+    for line in out.splitlines():
+        if line.startswith("FAILED") and any(k in line for k in ("test_mxm", "test_mxv", "test_vxm", "test_RC")):
+            assert "Panic" in line, line
