@@ -42,7 +42,7 @@ def declared_symbols():
     """Every function / global object name the headers declare (used by the ABI test)."""
     cdef = header_cdef()
     names = set(re.findall(r"\b((?:GrB|GxB|B200)_\w+)\s*\(", cdef))
-    for decl in re.findall(r"extern\s+\w+\s+([^;]+);", cdef):
+    for decl in re.findall(r"extern\s+(?:const\s+)?\w+\s+([^;]+);", cdef):
         for n in decl.split(","):
             names.add(n.strip().lstrip("*"))
     # enum constants and typedef names are not symbols
