@@ -594,24 +594,27 @@ __global__ void __launch_bounds__(512) masked_spa_kernel(const MaskedArgs ma) {
 
 // per-row chunk counts: class 1 rows (warp kernel) get 0 chunks
 __global__ void chunk_count_kernel(const int64_t *flops, const uint32_t *m_ptr, int64_t nrows, int64_t chunk_flops,
-                                   int warp_flops, int warp_mlen, int medium_mlen, int64_t *cnt_medium, int64_t *cnt_long, int64_t *cls1) {
+                                   int warp_flops, int warp_mlen, int small_mlen, int medium_mlen, int64_t *cnt_small, int64_t *cnt_medium, int64_t *cnt_long, int64_t *cls1) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
         const int64_t f = flops[r]; const int64_t ml = m_ptr[r + 1] - m_ptr[r];
-        int64_t cm = 0, cl = 0, c1 = 0;
+        int64_t cs = 0, cm = 0, cl = 0, c1 = 0;
         if (f > 0 && ml > 0) {
             if (f <= warp_flops && ml <= warp_mlen) c1 = 1;
+            else if (ml <= small_mlen) cs = (f + chunk_flops - 1) / chunk_flops;
             else if (ml <= medium_mlen) cm = (f + chunk_flops - 1) / chunk_flops;
             else cl = (f + chunk_flops - 1) / chunk_flops;
         }
-        cnt_medium[r] = cm; cnt_long[r] = cl; cls1[r] = c1;
+        cnt_small[r] = cs; cnt_medium[r] = cm; cnt_long[r] = cl; cls1[r] = c1;
     }
 }
 // after exclusive scans of the three arrays: emit the chunk lists and the class-1 row list
-__global__ void chunk_fill_kernel(const int64_t *off_medium, const int64_t *off_long, const int64_t *off_cls1, int64_t nrows,
+__global__ void chunk_fill_kernel(const int64_t *off_small, const int64_t *off_medium, const int64_t *off_long, const int64_t *off_cls1, int64_t nrows,
+                                  int32_t *s_row, uint32_t *s_idx, uint32_t *s_cnt,
                                   int32_t *m_row, uint32_t *m_idx, uint32_t *m_cnt,
                                   int32_t *l_row, uint32_t *l_idx, uint32_t *l_cnt, int32_t *w_rows) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t cm = off_medium[r + 1] - off_medium[r], cl = off_long[r + 1] - off_long[r];
+        const int64_t cs = off_small[r + 1] - off_small[r], cm = off_medium[r + 1] - off_medium[r], cl = off_long[r + 1] - off_long[r];
+        for (int64_t c = 0; c < cs; ++c) { const int64_t o = off_small[r] + c; s_row[o] = (int32_t)r; s_idx[o] = (uint32_t)c; s_cnt[o] = (uint32_t)cs; }
         for (int64_t c = 0; c < cm; ++c) { const int64_t o = off_medium[r] + c; m_row[o] = (int32_t)r; m_idx[o] = (uint32_t)c; m_cnt[o] = (uint32_t)cm; }
         for (int64_t c = 0; c < cl; ++c) { const int64_t o = off_long[r] + c; l_row[o] = (int32_t)r; l_idx[o] = (uint32_t)c; l_cnt[o] = (uint32_t)cl; }
         if (off_cls1[r + 1] > off_cls1[r]) w_rows[off_cls1[r]] = (int32_t)r;
@@ -775,6 +778,7 @@ static bool op_uses_y(int op) { return !(op == OP_FIRST || op == OP_PAIR || op =
 
 static constexpr int SMALL_TABLE = 256, SMALL_FLOPS = 128;      // warp per row
 static constexpr int MEDIUM_TABLE = 4096, MEDIUM_FLOPS = 2048;  // CTA per row
+static constexpr int MIDSMALL_TABLE = 1024;                       // masked: CTA per chunk, mask rows up to 512 entries
 
 // dispatch helpers: KERNEL is a macro taking (XT, ZT, ADD, MUL)
 #define GB_FOR_SEMIRING(xt, zt, add, mul, KERNEL, err)                                                        \
@@ -955,28 +959,40 @@ static GrB_Info spgemm_masked(const Csr &A, const Csr &B, const void *aval, cons
 #define K_IDENT(XT, ZT, A_, M_) spa_fill_identity<ZT>(words, M.nnz, (A_) >= 0 ? (A_) : add)
         GB_FOR_SEMIRING(xt, zt, add, mul, K_IDENT, err); GB_LAUNCHED();
         // classify rows and cut heavy ones into flop-bounded chunks
-        int64_t *cm = nullptr, *cl = nullptr, *c1 = nullptr;
+        int64_t *cs = nullptr, *cm = nullptr, *cl = nullptr, *c1 = nullptr;
+        GB_TRY(dalloc(&cs, (size_t)nrows + 1, err));
         GB_TRY(dalloc(&cm, (size_t)nrows + 1, err)); GB_TRY(dalloc(&cl, (size_t)nrows + 1, err)); GB_TRY(dalloc(&c1, (size_t)nrows + 1, err));
+        CU_TRY(cudaMemsetAsync(cs + nrows, 0, 8, G.stream), err);
         CU_TRY(cudaMemsetAsync(cm + nrows, 0, 8, G.stream), err); CU_TRY(cudaMemsetAsync(cl + nrows, 0, 8, G.stream), err);
         CU_TRY(cudaMemsetAsync(c1 + nrows, 0, 8, G.stream), err);
         chunk_count_kernel<<<grid_for(nrows), 256, 0, G.stream>>>(flops, M.rowptr32, nrows, CHUNK_FLOPS, WARP_FLOPS, SMALL_TABLE / 2,
-                                                                  MEDIUM_TABLE / 2, cm, cl, c1); GB_LAUNCHED();
+                                                                  MIDSMALL_TABLE / 2, MEDIUM_TABLE / 2, cs, cm, cl, c1); GB_LAUNCHED();
+        GB_TRY(dev_exclusive_scan(cs, nrows + 1, err));
         GB_TRY(dev_exclusive_scan(cm, nrows + 1, err)); GB_TRY(dev_exclusive_scan(cl, nrows + 1, err)); GB_TRY(dev_exclusive_scan(c1, nrows + 1, err));
-        int64_t n_medium = 0, n_long = 0, n_warp = 0, tf = 0;
+        int64_t n_small = 0, n_medium = 0, n_long = 0, n_warp = 0, tf = 0;
+        GB_TRY(read_i64(cs + nrows, &n_small, err));
         GB_TRY(read_i64(cm + nrows, &n_medium, err)); GB_TRY(read_i64(cl + nrows, &n_long, err)); GB_TRY(read_i64(c1 + nrows, &n_warp, err));
         GB_TRY(read_i64((const int64_t *)total, &tf, err));
         G.last_flops = (uint64_t)tf;
-        int32_t *m_row = nullptr, *l_row = nullptr, *w_rows = nullptr; uint32_t *m_idx = nullptr, *m_cnt = nullptr, *l_idx = nullptr, *l_cnt = nullptr;
+        int32_t *s_row = nullptr, *m_row = nullptr, *l_row = nullptr, *w_rows = nullptr;
+        uint32_t *s_idx = nullptr, *s_cnt = nullptr, *m_idx = nullptr, *m_cnt = nullptr, *l_idx = nullptr, *l_cnt = nullptr;
+        GB_TRY(dalloc(&s_row, (size_t)n_small, err)); GB_TRY(dalloc(&s_idx, (size_t)n_small, err)); GB_TRY(dalloc(&s_cnt, (size_t)n_small, err));
         GB_TRY(dalloc(&m_row, (size_t)n_medium, err)); GB_TRY(dalloc(&m_idx, (size_t)n_medium, err)); GB_TRY(dalloc(&m_cnt, (size_t)n_medium, err));
         GB_TRY(dalloc(&l_row, (size_t)n_long, err)); GB_TRY(dalloc(&l_idx, (size_t)n_long, err)); GB_TRY(dalloc(&l_cnt, (size_t)n_long, err));
         GB_TRY(dalloc(&w_rows, (size_t)n_warp, err));
-        chunk_fill_kernel<<<grid_for(nrows), 256, 0, G.stream>>>(cm, cl, c1, nrows, m_row, m_idx, m_cnt, l_row, l_idx, l_cnt, w_rows); GB_LAUNCHED();
-        dfree(flops); dfree(total); dfree(cm); dfree(cl); dfree(c1);
+        chunk_fill_kernel<<<grid_for(nrows), 256, 0, G.stream>>>(cs, cm, cl, c1, nrows, s_row, s_idx, s_cnt, m_row, m_idx, m_cnt, l_row, l_idx, l_cnt, w_rows); GB_LAUNCHED();
+        dfree(flops); dfree(total); dfree(cs); dfree(cm); dfree(cl); dfree(c1);
         if (n_warp) {
             g.rows = w_rows; g.nbin = n_warp; g.table = SMALL_TABLE;
             const size_t sm = masked_smem(SMALL_TABLE, 8, wsize);
 #define K_MSMALL(XT, ZT, A_, M_) masked_hash_kernel<XT, ZT, A_, M_, true><<<(unsigned)ceil_div(n_warp, 8), 256, sm, G.stream>>>(ma)
             GB_FOR_SEMIRING(xt, zt, add, mul, K_MSMALL, err); GB_LAUNCHED();
+        }
+        if (n_small) {      // mask rows up to 512 entries: 1024-slot table, 12-16 KB of shared memory, twice the CTAs per SM
+            ma.chunk_row = s_row; ma.chunk_idx = s_idx; ma.chunk_cnt = s_cnt; ma.nchunks = n_small; g.table = MIDSMALL_TABLE;
+            const size_t sm = masked_smem(MIDSMALL_TABLE, 1, wsize);
+#define K_MMIDSMALL(XT, ZT, A_, M_) masked_hash_kernel<XT, ZT, A_, M_, false><<<(unsigned)n_small, 256, sm, G.stream>>>(ma)
+            GB_FOR_SEMIRING(xt, zt, add, mul, K_MMIDSMALL, err); GB_LAUNCHED();
         }
         if (n_medium) {
             ma.chunk_row = m_row; ma.chunk_idx = m_idx; ma.chunk_cnt = m_cnt; ma.nchunks = n_medium; g.table = MEDIUM_TABLE;
@@ -997,7 +1013,7 @@ static GrB_Info spgemm_masked(const Csr &A, const Csr &B, const void *aval, cons
             GB_FOR_SEMIRING(xt, zt, add, mul, K_MSPA, err); GB_LAUNCHED();
             dfree(g.spa_slot); dfree(g.queue);
         }
-        dfree(m_row); dfree(m_idx); dfree(m_cnt); dfree(l_row); dfree(l_idx); dfree(l_cnt); dfree(w_rows);
+        dfree(s_row); dfree(s_idx); dfree(s_cnt); dfree(m_row); dfree(m_idx); dfree(m_cnt); dfree(l_row); dfree(l_idx); dfree(l_cnt); dfree(w_rows);
         if (zsz < 4) {      // narrow 32-bit accumulator words to the 1- or 2-byte type, in a second buffer
             void *typed = nullptr;
             GB_TRY(dmalloc(&typed, (size_t)M.nnz * zsz + 16, err));
