@@ -873,38 +873,49 @@ __global__ void __launch_bounds__(256) spmv_masked_pull_kernel(const PullArgs p)
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const XT *aval = static_cast<const XT *>(p.aval), *uval = static_cast<const XT *>(p.uval);
     ZT *tval = static_cast<ZT *>(p.tval);
-    for (int64_t r = warp; r < p.nrows; r += nwarps) {
-        bool m = p.mpres ? p.mpres[r] != 0 : true;
-        if (m && !p.mask_struct) m = sc_cast(sc_load(p.mtc, p.mval, (size_t)r), p.mtc, TC_BOOL).u != 0;
-        if (p.mask_comp) m = !m;
-        if (!m) { if (lane == 0) p.tpres[r] = 0; continue; }
-        const uint32_t rs = p.rowptr[r], re = p.rowptr[r + 1];
-        Part<ZT> acc{(ZT)0, 0};
-        for (uint32_t base = rs; base < re; base += 128) {
+    for (int64_t base = warp * 32; base < p.nrows; base += nwarps * 32) {
+        // 32 rows per warp iteration: the lanes evaluate the mask of their own row (coalesced), rows the mask
+        // rules out cost nothing more than that
+        const int64_t mr = base + lane;
+        bool m = false;
+        if (mr < p.nrows) {
+            m = p.mpres ? p.mpres[mr] != 0 : true;
+            if (m && !p.mask_struct) m = sc_cast(sc_load(p.mtc, p.mval, (size_t)mr), p.mtc, TC_BOOL).u != 0;
+            if (p.mask_comp) m = !m;
+            if (!m) p.tpres[mr] = 0;
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, m);
+        while (todo) {
+            const int64_t r = base + (__ffs(todo) - 1);
+            todo &= todo - 1;
+            const uint32_t rs = p.rowptr[r], re = p.rowptr[r + 1];
+            Part<ZT> acc{(ZT)0, 0};
+            for (uint32_t b0 = rs; b0 < re; b0 += 128) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t k = base + q * 32 + lane;
-                if (k < re) {
-                    const uint32_t c = __ldg(p.col + k);
-                    if (!p.upres || __ldg(p.upres + c)) {
-                        const XT a = gload<XT>(aval + k), u = gload<XT>(uval + c);
-                        const Part<ZT> it{p.flip ? MulApply<XT, ZT>::f(p.mul_op, u, a) : MulApply<XT, ZT>::f(p.mul_op, a, u), 1};
-                        acc = part_join<ZT>(p.add_op, acc, it);
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t k = b0 + q * 32 + lane;
+                    if (k < re) {
+                        const uint32_t c = __ldg(p.col + k);
+                        if (!p.upres || __ldg(p.upres + c)) {
+                            const XT a = gload<XT>(aval + k), u = gload<XT>(uval + c);
+                            const Part<ZT> it{p.flip ? MulApply<XT, ZT>::f(p.mul_op, u, a) : MulApply<XT, ZT>::f(p.mul_op, a, u), 1};
+                            acc = part_join<ZT>(p.add_op, acc, it);
+                        }
                     }
                 }
+                if (__any_sync(0xffffffffu, acc.has && monoid_saturated<ZT>(p.add_op, acc.v))) break;
             }
-            if (__any_sync(0xffffffffu, acc.has && monoid_saturated<ZT>(p.add_op, acc.v))) break;
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            Part<ZT> y; y.v = shfl_xor_t<ZT>(acc.v, o); y.has = __shfl_xor_sync(0xffffffffu, acc.has, o);
-            acc = part_join<ZT>(p.add_op, acc, y);
+            for (int o = 16; o > 0; o >>= 1) {
+                Part<ZT> y; y.v = shfl_xor_t<ZT>(acc.v, o); y.has = __shfl_xor_sync(0xffffffffu, acc.has, o);
+                acc = part_join<ZT>(p.add_op, acc, y);
+            }
+            if (lane == 0) { tval[r] = acc.v; p.tpres[r] = (uint8_t)acc.has; }
         }
-        if (lane == 0) { tval[r] = acc.v; p.tpres[r] = (uint8_t)acc.has; }
     }
 }
 static GrB_Info spmv_masked_pull_dispatch(int xt, int zt, const PullArgs &a, std::string *err) {
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a.nrows * 32, 256), (int64_t)G.num_sms * 8));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a.nrows, 256), (int64_t)G.num_sms * 8));
 #define GB_PULL(XT_, ZT_) do { spmv_masked_pull_kernel<XT_, ZT_><<<grid, 256, 0, G.stream>>>(a); GB_LAUNCHED(); return GrB_SUCCESS; } while (0)
     if (xt == zt) {
         switch (xt) {
