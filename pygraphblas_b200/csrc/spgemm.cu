@@ -440,14 +440,20 @@ __device__ __forceinline__ void flat_stream(const GemmArgs &p, uint32_t c0, uint
             int lo = 0, hi = nent - 1;                       // largest e with s_off[e] <= f0
             while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= f0) lo = mid; else hi = mid - 1; }
             int e = lo;
+            // locate the run's positions first, then issue all its column loads back to back, then probe
+            uint32_t pbv[RUN], jv[RUN]; XT avv[RUN]; int cnt = 0;
 #pragma unroll
             for (uint32_t i = 0; i < RUN; ++i) {
                 const uint32_t f = f0 + i;
-                if (f >= (uint32_t)total) break;
-                while (e + 1 < nent && s_off[e + 1] <= f) ++e;
-                const uint32_t pb = s_bs[e] + (f - s_off[e]);
-                hit(__ldg(p.b_col + pb), s_av[e], pb);
+                if (f < (uint32_t)total) {
+                    while (e + 1 < nent && s_off[e + 1] <= f) ++e;
+                    pbv[i] = s_bs[e] + (f - s_off[e]); avv[i] = s_av[e]; cnt = (int)i + 1;
+                }
             }
+#pragma unroll
+            for (uint32_t i = 0; i < RUN; ++i) if ((int)i < cnt) jv[i] = __ldg(p.b_col + pbv[i]);
+#pragma unroll
+            for (uint32_t i = 0; i < RUN; ++i) if ((int)i < cnt) hit(jv[i], avv[i], pbv[i]);
         }
         __syncthreads();
     }

@@ -394,12 +394,16 @@ struct RunArgs {
     int64_t nruns; int64_t nnz;
     void *tval;
     void *head_val; void *tail_val;                            // per run: partial of the row it starts inside / of the row open at its end
+    int add_op, mul_op, flip;                                  // run-time operator codes (kernels instantiated with ADD = MUL = -1)
 };
 
-template <typename XT, typename ZT, int ADD, int MUL, bool HOT>
+template <typename XT, typename ZT, int ADD_C, int MUL_C, bool HOT>
 __device__ __forceinline__ void spmv_run_body(const RunArgs &p, const int64_t run, const int lane, const XT *s_hot, const uint32_t hot_n) {
-    constexpr bool NEED_A = mul_reads_x(MUL);
-    constexpr bool NEED_U = mul_reads_y(MUL);
+    // ADD_C / MUL_C >= 0: compile-time semiring; -1: run-time operator codes (both operands are read)
+    constexpr bool NEED_A = MUL_C < 0 || mul_reads_x(MUL_C);
+    constexpr bool NEED_U = MUL_C < 0 || mul_reads_y(MUL_C);
+    const int ADD = ADD_C >= 0 ? ADD_C : p.add_op;
+    const int MUL = MUL_C >= 0 ? MUL_C : p.mul_op;
     const int64_t q = run * RUN + lane * 8;
     const int nvalid = (int)min((int64_t)8, max((int64_t)0, p.nnz - q));
     const XT *uval = static_cast<const XT *>(p.uval);
@@ -428,7 +432,10 @@ __device__ __forceinline__ void spmv_run_body(const RunArgs &p, const int64_t ru
     }
     ZT prod[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) prod[j] = MulApply<XT, ZT>::f(MUL, NEED_A ? a[j] : (XT)1, NEED_U ? uv[j] : (XT)1);
+    for (int j = 0; j < 8; ++j) {
+        const XT av = NEED_A ? a[j] : (XT)1, uu = NEED_U ? uv[j] : (XT)1;
+        prod[j] = (MUL_C < 0 && p.flip) ? MulApply<XT, ZT>::f(MUL, uu, av) : MulApply<XT, ZT>::f(MUL, av, uu);
+    }
 
     // ---- fold between row starts
     Part<ZT> acc{(ZT)0, 0}, lead{(ZT)0, 0};
@@ -504,8 +511,9 @@ __global__ void __launch_bounds__(THREADS, MINB) spmv_run_hot_kernel(const RunAr
 
 // rows that continue past their run: tail partial (+) head partials of the following runs, 8 lanes per open row.
 // Every run after `run` up to tail_last starts inside that row, so its head partial exists.
-template <typename ZT, int ADD>
+template <typename ZT, int ADD_C>
 __global__ void __launch_bounds__(256) spmv_run_fixup_kernel(const RunArgs p) {
+    const int ADD = ADD_C >= 0 ? ADD_C : p.add_op;
     const int sub = threadIdx.x & 7;
     const int64_t run = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const int32_t r = run < p.nruns ? __ldg(p.tail_row + run) : -1;
@@ -606,7 +614,7 @@ static GrB_Info spmv_run_plan(Csr &c, std::string *err) {
 
 template <typename XT, typename ZT, int ADD, int MUL>
 static void spmv_run_launch(const RunArgs &a, size_t hot_bytes, int64_t hused) {
-    if (hot_bytes) {
+    if (hot_bytes && ADD >= 0) {
         // two shapes: one 1024-thread CTA per SM with a table of up to ~200 KB, or two 768-thread CTAs
         // per SM (<= 42 registers) with a table of up to ~100 KB each
         const bool two = hot_bytes <= ((size_t)104 << 10) && getenv("B200GRB_HOT_ONE") == nullptr;
@@ -638,6 +646,28 @@ static bool spmv_run_fast_bool(int add, int mul, const RunArgs &a, size_t hot_by
 #define GB_FAST(A, M) if (add == A && mul == M) { spmv_run_launch<bool, bool, A, M>(a, hot_bytes, hused); return true; }
     GB_FAST(OP_LOR, OP_LAND) GB_FAST(OP_ANY, OP_PAIR) GB_FAST(OP_LOR, OP_PAIR) GB_FAST(OP_LOR, OP_SECOND) GB_FAST(OP_LOR, OP_FIRST)
 #undef GB_FAST
+    return false;
+}
+static bool spmv_run_generic(int xt, int zt, const RunArgs &a) {
+#define GB_RUNGEN(XT_, ZT_) do { spmv_run_launch<XT_, ZT_, -1, -1>(a, 0, 0); return true; } while (0)
+    if (xt == zt) {
+        switch (xt) {
+#define GB_GEN(TC, T) case TC: GB_RUNGEN(T, T);
+            GB_GEN(TC_BOOL, bool) GB_GEN(TC_INT8, int8_t) GB_GEN(TC_INT16, int16_t) GB_GEN(TC_INT32, int32_t) GB_GEN(TC_INT64, int64_t)
+            GB_GEN(TC_UINT8, uint8_t) GB_GEN(TC_UINT16, uint16_t) GB_GEN(TC_UINT32, uint32_t) GB_GEN(TC_UINT64, uint64_t)
+            GB_GEN(TC_FP32, float) GB_GEN(TC_FP64, double)
+#undef GB_GEN
+        }
+    } else if (zt == TC_BOOL) {
+        switch (xt) {
+#define GB_GEN(TC, T) case TC: GB_RUNGEN(T, bool);
+            GB_GEN(TC_INT8, int8_t) GB_GEN(TC_INT16, int16_t) GB_GEN(TC_INT32, int32_t) GB_GEN(TC_INT64, int64_t)
+            GB_GEN(TC_UINT8, uint8_t) GB_GEN(TC_UINT16, uint16_t) GB_GEN(TC_UINT32, uint32_t) GB_GEN(TC_UINT64, uint64_t)
+            GB_GEN(TC_FP32, float) GB_GEN(TC_FP64, double)
+#undef GB_GEN
+        }
+    }
+#undef GB_RUNGEN
     return false;
 }
 static bool spmv_run_dispatch(int xt, int add, int mul, const RunArgs &a, size_t hot_bytes, int64_t hused) {
@@ -1049,8 +1079,9 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
         if (r != GrB_SUCCESS) { dfree(tval); dfree(tpres); dfree(a_cast); dfree(u_cast); return r; }
     }
     // dense u + specialised semiring: warp-independent run kernel on the cached run plan
-    bool use_run = !use_pull && fast && c.nnz >= 4096;
-    if (const char *e = getenv("B200GRB_SPMV_RUN")) use_run = !use_pull && fast && c.nnz > 0 && atoi(e) != 0;
+    const bool run_ok = !use_pull && !sparse_u && (fast || xt == zt || zt == TC_BOOL);     // dense u: specialised or run-time operators
+    bool use_run = run_ok && c.nnz >= 4096;
+    if (const char *e = getenv("B200GRB_SPMV_RUN")) use_run = run_ok && c.nnz > 0 && atoi(e) != 0;
     if (use_pull) {
         // done above
     } else if (use_run) {
@@ -1061,6 +1092,7 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
         ra.col = c.col; ra.aval = aval; ra.uval = uval; ra.headw = c.run_headw; ra.lane_rank = c.run_lane; ra.run_base = c.run_base;
         ra.nzrow = c.nzrow; ra.rowptr = c.rowptr32; ra.nruns = c.nruns; ra.nnz = c.nnz; ra.tval = tval;
         ra.tail_row = c.run_tail_row; ra.tail_last = c.run_tail_last;
+        ra.add_op = add; ra.mul_op = kmul; ra.flip = kflip;
         GB_TRY(dmalloc(&ra.head_val, (size_t)c.nruns * zsz + 16, err));
         GB_TRY(dmalloc(&ra.tail_val, (size_t)c.nruns * zsz + 16, err));
         void *u_perm = nullptr; size_t hot_bytes = 0;
@@ -1068,7 +1100,7 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
         // B200GRB_SPMV_HOT=0 disables it, =<KB> forces a table size
         const char *hot_env = getenv("B200GRB_SPMV_HOT");
         int hot_kb = hot_env ? atoi(hot_env) : 160;
-        if (need_u && hot_kb > 0 && c.nnz >= ((int64_t)1 << 20) && c.ncols >= (1 << 16)) {
+        if (fast && need_u && hot_kb > 0 && c.nnz >= ((int64_t)1 << 20) && c.ncols >= (1 << 16)) {
             GB_TRY(spmv_hot_plan(c, err));
             if (!hot_env && c.hot_cover < 0.25) hot_kb = 0;
         } else hot_kb = 0;
@@ -1078,7 +1110,7 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
             if (c.hused > 0) { permute_u_kernel<<<hgrid(c.hused), 256, 0, G.stream>>>(c.hperm, (const uint8_t *)uval, (uint8_t *)u_perm, (int)xsz, c.hused); GB_LAUNCHED(); }
             ra.col = c.hcol; ra.uval = u_perm; hot_bytes = (size_t)hot_kb << 10;
         }
-        const bool ok = spmv_run_dispatch(xt, add, kmul, ra, hot_bytes, c.hused);
+        const bool ok = fast ? spmv_run_dispatch(xt, add, kmul, ra, hot_bytes, c.hused) : spmv_run_generic(xt, zt, ra);
         dfree(u_perm); dfree(ra.head_val); dfree(ra.tail_val);
         if (!ok) { dfree(tval); dfree(tpres); dfree(a_cast); dfree(u_cast); return gb_fail(GrB_PANIC, err, "mxv: internal dispatch error"); }
     } else if (c.nnz == 0) {
