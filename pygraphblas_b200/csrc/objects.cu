@@ -494,20 +494,44 @@ GrB_Info vector_ensure_host(GrB_Vector v) {
     return GrB_SUCCESS;
 }
 
+__global__ void vec_scatter_kernel(const uint64_t *idx, const uint8_t *x, uint8_t *val, uint8_t *pres, int sz, int64_t k) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < k; q += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = idx[q];
+        for (int b = 0; b < sz; ++b) val[i * sz + b] = x[q * sz + b];
+        pres[i] = 1;
+    }
+}
 GrB_Info vector_ensure_device(GrB_Vector v) {
     if (!G.have_device) return gb_fail(GrB_PANIC, &v->err, "no CUDA device: libb200grb computes only on the GPU (no CPU fallback)");
     if (v->host_valid) GB_TRY(vector_flush_pending(v));
     if (v->dev_valid) return GrB_SUCCESS;
     if (v->n > DEV_DIM_MAX) return gb_fail(GrB_INVALID_VALUE, &v->err, "vector size %llu exceeds the 2^31-1 limit of the HBM layout", (unsigned long long)v->n);
-    const size_t sz = v->type->size, n = (size_t)v->n;
-    std::vector<uint8_t> vals(n * sz, 0), pres(n, 0);
-    for (size_t k = 0; k < v->hi.size(); ++k) { memcpy(&vals[v->hi[k] * sz], &v->hx[k * sz], sz); pres[v->hi[k]] = 1; }
+    const size_t sz = v->type->size, n = (size_t)v->n, k = v->hi.size();
     GB_TRY(dmalloc(&v->dval, n * sz + 16, &v->err));
-    const bool full = v->hi.size() == n && n > 0;
+    const bool full = k == n && n > 0;
     if (!full) GB_TRY(dmalloc((void **)&v->dpres, n + 16, &v->err));
-    if (n) {
+    if (n && k < n / 8) {
+        // few entries (a BFS source, a seed set): ship the tuples and scatter them in HBM rather than two dense arrays
+        CU_TRY(cudaMemsetAsync(v->dval, 0, n * sz, G.stream), &v->err);
+        CU_TRY(cudaMemsetAsync(v->dpres, 0, n, G.stream), &v->err);
+        if (k) {
+            uint64_t *di = nullptr; void *dx = nullptr;
+            GB_TRY(dmalloc((void **)&di, k * sizeof(uint64_t), &v->err));
+            GB_TRY(dmalloc(&dx, k * sz, &v->err));
+            CU_TRY(cudaMemcpyAsync(di, v->hi.data(), k * sizeof(uint64_t), cudaMemcpyHostToDevice, G.stream), &v->err);
+            CU_TRY(cudaMemcpyAsync(dx, v->hx.data(), k * sz, cudaMemcpyHostToDevice, G.stream), &v->err);
+            const int grid = (int)std::min<size_t>((k + 255) / 256, 4096);
+            vec_scatter_kernel<<<grid, 256, 0, G.stream>>>(di, (const uint8_t *)dx, (uint8_t *)v->dval, v->dpres, (int)sz, (int64_t)k);
+            G.launches++;
+            CU_TRY(cudaGetLastError(), &v->err);
+            dfree(di); dfree(dx);
+        }
+    } else if (n) {
+        std::vector<uint8_t> vals(n * sz, 0), pres(full ? 0 : n, 0);
+        for (size_t q = 0; q < k; ++q) { memcpy(&vals[v->hi[q] * sz], &v->hx[q * sz], sz); if (!full) pres[v->hi[q]] = 1; }
         CU_TRY(cudaMemcpyAsync(v->dval, vals.data(), n * sz, cudaMemcpyHostToDevice, G.stream), &v->err);
         if (!full) CU_TRY(cudaMemcpyAsync(v->dpres, pres.data(), n, cudaMemcpyHostToDevice, G.stream), &v->err);
+        CU_TRY(cudaStreamSynchronize(G.stream), &v->err);      // the staging vectors die here
     }
     CU_TRY(cudaStreamSynchronize(G.stream), &v->err);
     v->dev_valid = true; v->dev_nvals = (int64_t)v->hi.size();

@@ -887,6 +887,8 @@ struct PullArgs {
     const void *mval; const uint8_t *mpres; int mtc; int mask_comp, mask_struct;
     void *tval; uint8_t *tpres;
     int add_op, mul_op, flip;
+    int has_long; int64_t long_cap;
+    uint32_t *long_rows; int *long_count;                      // work list of the rows left to the CTA-per-row kernel
 };
 template <typename ZT> __device__ __forceinline__ bool monoid_saturated(int add, ZT v) {
     switch (add) {
@@ -896,6 +898,39 @@ template <typename ZT> __device__ __forceinline__ bool monoid_saturated(int add,
         default: return false;
     }
 }
+template <typename T> __device__ __forceinline__ T shfl_idx_t(T v, int src) {
+    if constexpr (sizeof(T) == 8) { long long x = reinterpret_cast<long long &>(v); x = __shfl_sync(0xffffffffu, x, src); return reinterpret_cast<T &>(x); }
+    else if constexpr (sizeof(T) == 4) { int x = reinterpret_cast<int &>(v); x = __shfl_sync(0xffffffffu, x, src); return reinterpret_cast<T &>(x); }
+    else { int x = (int)v; x = __shfl_sync(0xffffffffu, x, src); return (T)x; }
+}
+// The three monoids of this kernel (LOR, LAND, ANY) need no running value: the fold of a row's products is
+// decided by how many there are (0, 1, more), whether one of them saturates, and the first one --
+//   0 products: no entry;  1: that product, as is;  more: ANY -> any of them, LOR -> "one was non-zero",
+//   LAND -> "none was zero" (1 or 0 in the monoid's type).
+// A row may stop early once its result can no longer change.
+template <typename ZT> __device__ __forceinline__ ZT pull_result(int add, int n, bool sat, ZT first) {
+    if (n <= 1 || add == OP_ANY) return first;
+    return add == OP_LOR ? (ZT)(sat ? 1 : 0) : (ZT)(sat ? 0 : 1);
+}
+template <typename ZT> __device__ __forceinline__ bool pull_settled(int add, ZT v) {     // saturating AND already the final value
+    switch (add) {
+        case OP_LOR: return v == (ZT)1;
+        case OP_LAND: return v == (ZT)0;
+        case OP_ANY: return true;
+        default: return false;
+    }
+}
+template <typename XT, typename ZT>
+__device__ __forceinline__ ZT pull_product(const PullArgs &p, const XT *aval, const XT *uval, uint32_t k, uint32_t c) {
+    const XT a = gload<XT>(aval + k), u = gload<XT>(uval + c);
+    return p.flip ? MulApply<XT, ZT>::f(p.mul_op, u, a) : MulApply<XT, ZT>::f(p.mul_op, a, u);
+}
+constexpr uint32_t PULL_LONG = 4096;          // rows longer than this go to the CTA-per-row kernel
+
+// Warp batches of 32 rows, their entries flattened: lane i owns row base+i (mask, accumulators, result) while
+// the entries of all 32 rows are walked 32 at a time, so short rows cost one slot per entry instead of one
+// warp iteration per row.  Rows advance in rounds of at most `cap` entries each; a row whose result is settled
+// leaves the batch at the end of the round.
 template <typename XT, typename ZT>
 __global__ void __launch_bounds__(256) spmv_masked_pull_kernel(const PullArgs p) {
     const int lane = threadIdx.x & 31;
@@ -903,9 +938,8 @@ __global__ void __launch_bounds__(256) spmv_masked_pull_kernel(const PullArgs p)
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const XT *aval = static_cast<const XT *>(p.aval), *uval = static_cast<const XT *>(p.uval);
     ZT *tval = static_cast<ZT *>(p.tval);
+    const int add = p.add_op;
     for (int64_t base = warp * 32; base < p.nrows; base += nwarps * 32) {
-        // 32 rows per warp iteration: the lanes evaluate the mask of their own row (coalesced), rows the mask
-        // rules out cost nothing more than that
         const int64_t mr = base + lane;
         bool m = false;
         if (mr < p.nrows) {
@@ -914,39 +948,98 @@ __global__ void __launch_bounds__(256) spmv_masked_pull_kernel(const PullArgs p)
             if (p.mask_comp) m = !m;
             if (!m) p.tpres[mr] = 0;
         }
-        unsigned todo = __ballot_sync(0xffffffffu, m);
-        while (todo) {
-            const int64_t r = base + (__ffs(todo) - 1);
-            todo &= todo - 1;
-            const uint32_t rs = p.rowptr[r], re = p.rowptr[r + 1];
-            Part<ZT> acc{(ZT)0, 0};
-            for (uint32_t b0 = rs; b0 < re; b0 += 128) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t k = b0 + q * 32 + lane;
-                    if (k < re) {
-                        const uint32_t c = __ldg(p.col + k);
-                        if (!p.upres || __ldg(p.upres + c)) {
-                            const XT a = gload<XT>(aval + k), u = gload<XT>(uval + c);
-                            const Part<ZT> it{p.flip ? MulApply<XT, ZT>::f(p.mul_op, u, a) : MulApply<XT, ZT>::f(p.mul_op, a, u), 1};
-                            acc = part_join<ZT>(p.add_op, acc, it);
-                        }
-                    }
-                }
-                if (__any_sync(0xffffffffu, acc.has && monoid_saturated<ZT>(p.add_op, acc.v))) break;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                Part<ZT> y; y.v = shfl_xor_t<ZT>(acc.v, o); y.has = __shfl_xor_sync(0xffffffffu, acc.has, o);
-                acc = part_join<ZT>(p.add_op, acc, y);
-            }
-            if (lane == 0) { tval[r] = acc.v; p.tpres[r] = (uint8_t)acc.has; }
+        uint32_t pos = 0, rem = 0;
+        if (m) {
+            pos = p.rowptr[mr]; rem = p.rowptr[mr + 1] - pos;
+            if (rem > PULL_LONG) { p.long_rows[atomicAdd(p.long_count, 1)] = (uint32_t)mr; rem = 0; m = false; }
         }
+        int n_it = 0; bool sat = false; ZT first = (ZT)0;
+        unsigned active;
+        while ((active = __ballot_sync(0xffffffffu, rem > 0)) != 0) {
+            const uint32_t cap = __popc(active) > 8 ? 32u : 128u;
+            const uint32_t take = rem < cap ? rem : cap;
+            uint32_t incl = take;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const uint32_t off = incl - take, total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t delta = pos - off;                  // entry index = delta(owner) + flat position
+            for (uint32_t f0 = 0; f0 < total; f0 += 32) {
+                const uint32_t f = f0 + lane;
+                int own = 0;                                   // first lane whose inclusive end exceeds f
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) { const uint32_t t = __shfl_sync(0xffffffffu, incl, own + step - 1); if (t <= f) own += step; }
+                const uint32_t k = __shfl_sync(0xffffffffu, delta, own) + f;
+                bool has = false; ZT v = (ZT)0;
+                if (f < total) {
+                    const uint32_t c = __ldg(p.col + k);
+                    if (!p.upres || __ldg(p.upres + c)) { v = pull_product<XT, ZT>(p, aval, uval, k, c); has = true; }
+                }
+                const unsigned hasmask = __ballot_sync(0xffffffffu, has);
+                const unsigned satmask = __ballot_sync(0xffffffffu, has && monoid_saturated<ZT>(add, v));
+                // the slots of this chunk that belong to this lane's row
+                const uint32_t s0 = off > f0 ? off : f0, s1 = (off + take) < (f0 + 32) ? (off + take) : (f0 + 32);
+                unsigned seg = 0;
+                if (s1 > s0) { const uint32_t len = s1 - s0; seg = (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << (s0 - f0); }
+                const unsigned mine = hasmask & seg;
+                const ZT fv = shfl_idx_t<ZT>(v, mine ? __ffs(mine) - 1 : lane);
+                if (mine) {
+                    if (n_it == 0) first = fv;
+                    n_it = min(2, n_it + __popc(mine));
+                    sat |= (satmask & seg) != 0;
+                }
+            }
+            if (sat && (n_it >= 2 || pull_settled<ZT>(add, first))) rem = 0;
+            else { rem -= take; pos += take; }
+        }
+        if (m) { tval[mr] = pull_result<ZT>(add, n_it, sat, first); p.tpres[mr] = (uint8_t)(n_it > 0); }
+    }
+}
+// Long rows (hubs): one 1024-thread CTA per row, 1024 entries per iteration, early exit CTA-wide.
+template <typename XT, typename ZT>
+__global__ void __launch_bounds__(1024) spmv_pull_long_kernel(const PullArgs p) {
+    __shared__ int s_n[32]; __shared__ int s_sat[32]; __shared__ ZT s_first[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const XT *aval = static_cast<const XT *>(p.aval), *uval = static_cast<const XT *>(p.uval);
+    ZT *tval = static_cast<ZT *>(p.tval);
+    const int add = p.add_op;
+    const int nlong = *p.long_count;
+    for (int w = blockIdx.x; w < nlong; w += gridDim.x) {
+        const uint32_t r = p.long_rows[w];
+        const uint32_t rs = p.rowptr[r], re = p.rowptr[r + 1];
+        int n_it = 0; bool sat = false; ZT first = (ZT)0;
+        for (uint32_t b0 = rs; b0 < re; b0 += 1024) {
+            const uint32_t k = b0 + threadIdx.x;
+            int stop = 0;
+            if (k < re) {
+                const uint32_t c = __ldg(p.col + k);
+                if (!p.upres || __ldg(p.upres + c)) {
+                    const ZT v = pull_product<XT, ZT>(p, aval, uval, k, c);
+                    if (n_it == 0) first = v;
+                    n_it = min(2, n_it + 1);
+                    if (monoid_saturated<ZT>(add, v)) { sat = true; stop = pull_settled<ZT>(add, v); }
+                }
+            }
+            if (__syncthreads_or(stop)) break;
+        }
+        const unsigned hasmask = __ballot_sync(0xffffffffu, n_it > 0);
+        const int wn = min(2, __reduce_add_sync(0xffffffffu, n_it));
+        const int wsat = __any_sync(0xffffffffu, sat);
+        const ZT wfirst = shfl_idx_t<ZT>(first, hasmask ? __ffs(hasmask) - 1 : 0);
+        if (lane == 0) { s_n[wid] = wn; s_sat[wid] = wsat; s_first[wid] = wfirst; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int N = 0, S = 0; ZT F = (ZT)0;
+            for (int q = 0; q < 32; ++q) { if (s_n[q] && !N) F = s_first[q]; N = min(2, N + s_n[q]); S |= s_sat[q]; }
+            tval[r] = pull_result<ZT>(add, N, S != 0, F); p.tpres[r] = (uint8_t)(N > 0);
+        }
+        __syncthreads();
     }
 }
 static GrB_Info spmv_masked_pull_dispatch(int xt, int zt, const PullArgs &a, std::string *err) {
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a.nrows, 256), (int64_t)G.num_sms * 8));
-#define GB_PULL(XT_, ZT_) do { spmv_masked_pull_kernel<XT_, ZT_><<<grid, 256, 0, G.stream>>>(a); GB_LAUNCHED(); return GrB_SUCCESS; } while (0)
+    const int lgrid = (int)std::max<int64_t>(1, std::min<int64_t>(a.long_cap, (int64_t)G.num_sms * 2));
+#define GB_PULL(XT_, ZT_) do { spmv_masked_pull_kernel<XT_, ZT_><<<grid, 256, 0, G.stream>>>(a); GB_LAUNCHED(); \
+        if (a.has_long) { spmv_pull_long_kernel<XT_, ZT_><<<lgrid, 1024, 0, G.stream>>>(a); GB_LAUNCHED(); } return GrB_SUCCESS; } while (0)
     if (xt == zt) {
         switch (xt) {
 #define GB_GEN(TC, T) case TC: GB_PULL(T, T);
@@ -1075,7 +1168,13 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
         pa.rowptr = c.rowptr32; pa.col = c.col; pa.aval = aval; pa.nrows = c.nrows; pa.uval = uval; pa.upres = u->dpres;
         pa.mval = mask->dval; pa.mpres = mask->dpres; pa.mtc = mask->type->code; pa.mask_comp = f.mask_comp; pa.mask_struct = f.mask_struct;
         pa.tval = tval; pa.tpres = tpres; pa.add_op = add; pa.mul_op = kmul; pa.flip = kflip;
+        // rows longer than PULL_LONG: at most nnz / PULL_LONG of them
+        pa.long_cap = c.nnz / (int64_t)PULL_LONG + 1; pa.has_long = c.nnz > (int64_t)PULL_LONG;
+        GB_TRY(dalloc(&pa.long_rows, (size_t)pa.long_cap + 1, err));
+        GB_TRY(dalloc(&pa.long_count, 4, err));
+        CU_TRY(cudaMemsetAsync(pa.long_count, 0, sizeof(int), G.stream), err);
         GrB_Info r = spmv_masked_pull_dispatch(xt, zt, pa, err);
+        dfree(pa.long_rows); dfree(pa.long_count);
         if (r != GrB_SUCCESS) { dfree(tval); dfree(tpres); dfree(a_cast); dfree(u_cast); return r; }
     }
     // dense u + specialised semiring: warp-independent run kernel on the cached run plan

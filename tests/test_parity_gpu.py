@@ -210,6 +210,38 @@ def test_rmat_bfs_levels_match_scipy():
     assert np.array_equal(level, ref)
 
 
+PULL_CASES = [("LOR", "LAND", "BOOL"), ("LAND", "LOR", "BOOL"), ("ANY", "PAIR", "BOOL"), ("LOR", "GT", "INT32"), ("LAND", "EQ", "FP32"),
+              ("LOR", "FIRST", "BOOL"), ("ANY", "PAIR", "INT64"), ("LAND", "SECOND", "BOOL")]
+
+
+@pytest.mark.parametrize("k", range(len(PULL_CASES) * 3))
+def test_masked_pull_hub_rows_against_oracle(k):
+    """The masked saturating-monoid kernel pair: batches of short rows, rows over 4096 entries (CTA-per-row
+    kernel), empty rows, sparse and dense u, every mask flavour."""
+    sr = PULL_CASES[k % len(PULL_CASES)]
+    rng = np.random.default_rng(7000 + k)
+    n = 9000
+    typ = sr[2]
+    hubs = rng.choice(n, 3, replace=False)
+    I = [np.full(d, h) for h, d in zip(hubs, (8500, 5000, 4097))]
+    J = [rng.choice(n, len(x), replace=False) for x in I]
+    short_rows = rng.choice(n, 5000, replace=False)
+    deg = rng.integers(1, 40, len(short_rows))
+    I.append(np.repeat(short_rows, deg)); J.append(rng.integers(0, n, int(deg.sum())))
+    I, J = np.concatenate(I), np.concatenate(J)
+    key = np.unique(I.astype(np.int64) * n + J)
+    I, J = np.divmod(key, n)
+    A = {"type": typ, "nrows": n, "ncols": n, "I": I.tolist(), "J": J.tolist(), "X": util.rand_values(rng, typ, len(I)).tolist()}
+    u = util.rand_vec(rng, typ, n, [0.001, 0.05, 1.0][k % 3])
+    desc = ["RC", "C", "S", "", "RSC", "SC"][k % 6]
+    mask = util.rand_vec(rng, ["BOOL", "UINT8", "FP32"][k % 3], n, 0.5)
+    w = util.rand_vec(rng, "BOOL" if sr[0] != "ANY" else typ, n, 0.3)
+    case = {"op": "mxv" if k % 2 == 0 else "vxm", "A": A, "u": u, "w": w, "mask": mask, "accum": None, "semiring": list(sr), "desc": desc}
+    if case["op"] == "vxm":
+        case["A"] = dict(A, I=A["J"], J=A["I"])
+    _check(case, util.product_run(case))
+
+
 def test_rmat_triangle_count_masked_mxm():
     """configs[3] shape: C<L> = L (+.pair) L on the strict lower triangle of A + A' (masked hash SpGEMM),
     and the masked-dot form C<L> = L L' (descriptor ST1); both against the CPU port and scipy."""
