@@ -395,9 +395,11 @@ struct RunArgs {
     void *tval;
     void *head_val; void *tail_val;                            // per run: partial of the row it starts inside / of the row open at its end
     int add_op, mul_op, flip;                                  // run-time operator codes (kernels instantiated with ADD = MUL = -1)
+    const uint8_t *upres;                                      // SPARSE kernels: presence bytes of u ...
+    uint8_t *tpres; uint8_t *head_has; uint8_t *tail_has;      // ... and of everything they produce
 };
 
-template <typename XT, typename ZT, int ADD_C, int MUL_C, bool HOT>
+template <typename XT, typename ZT, int ADD_C, int MUL_C, bool HOT, bool SPARSE = false>
 __device__ __forceinline__ void spmv_run_body(const RunArgs &p, const int64_t run, const int lane, const XT *s_hot, const uint32_t hot_n) {
     // ADD_C / MUL_C >= 0: compile-time semiring; -1: run-time operator codes (both operands are read)
     constexpr bool NEED_A = MUL_C < 0 || mul_reads_x(MUL_C);
@@ -422,8 +424,14 @@ __device__ __forceinline__ void spmv_run_body(const RunArgs &p, const int64_t ru
     const uint32_t hw = nvalid > 0 ? __ldg(p.headw + (q >> 5)) : 0u;
     const uint32_t hb = (hw >> ((lane & 3) * 8)) & 0xffu;                 // this lane's 8 row-start bits
     uint32_t rank = __ldg(p.run_base + run) + __ldg(p.lane_rank + run * 32 + lane);   // row starts before this lane's first entry
-    XT uv[8];
-    if (NEED_U) {
+    XT uv[8]; uint8_t up[8];
+    if (SPARSE) {
+        // u has holes: a product exists only where u(col) does; the values are fetched only for those
+#pragma unroll
+        for (int j = 0; j < 8; ++j) up[j] = j < nvalid ? __ldg(p.upres + c[j]) : (uint8_t)0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) uv[j] = (NEED_U && up[j]) ? gload<XT>(uval + c[j]) : (XT)0;
+    } else if (NEED_U) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (HOT && c[j] < hot_n) uv[j] = s_hot[c[j]];
@@ -440,7 +448,7 @@ __device__ __forceinline__ void spmv_run_body(const RunArgs &p, const int64_t ru
     // ---- fold between row starts
     Part<ZT> acc{(ZT)0, 0}, lead{(ZT)0, 0};
     bool seen = false; uint32_t cur = 0;
-    if (nvalid == 8) {
+    if (nvalid == 8 && !SPARSE) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if ((hb >> j) & 1u) {
@@ -456,10 +464,10 @@ __device__ __forceinline__ void spmv_run_body(const RunArgs &p, const int64_t ru
             if (j < nvalid) {
                 if ((hb >> j) & 1u) {
                     if (!seen) lead = acc;
-                    else tval[__ldg(p.nzrow + cur)] = acc.v;
+                    else { const uint32_t row = __ldg(p.nzrow + cur); tval[row] = acc.v; if (SPARSE) p.tpres[row] = (uint8_t)acc.has; }
                     seen = true; cur = rank++; acc.has = 0;
                 }
-                const Part<ZT> it{prod[j], 1};
+                const Part<ZT> it{prod[j], SPARSE ? (int)up[j] : 1};
                 acc = part_join<ZT>(ADD, acc, it);
             }
         }
@@ -484,17 +492,19 @@ __device__ __forceinline__ void spmv_run_body(const RunArgs &p, const int64_t ru
     // (which row that is, and where it ends, is structural: run_tail_row / run_tail_last of the plan)
     if (seen) {
         const Part<ZT> total = part_join<ZT>(ADD, acc, nxt);
-        if (nxt_stop) tval[__ldg(p.nzrow + cur)] = total.v;
-        else static_cast<ZT *>(p.tail_val)[run] = total.v;
+        if (nxt_stop) { const uint32_t row = __ldg(p.nzrow + cur); tval[row] = total.v; if (SPARSE) p.tpres[row] = (uint8_t)total.has; }
+        else { static_cast<ZT *>(p.tail_val)[run] = total.v; if (SPARSE) p.tail_has[run] = (uint8_t)total.has; }
     }
-    if (lane == 0 && !(hb & 1u) && nvalid > 0) static_cast<ZT *>(p.head_val)[run] = x.v;   // the run starts inside a row of an earlier run
+    if (lane == 0 && !(hb & 1u) && nvalid > 0) {                                            // the run starts inside a row of an earlier run
+        static_cast<ZT *>(p.head_val)[run] = x.v; if (SPARSE) p.head_has[run] = (uint8_t)x.has;
+    }
 }
 
-template <typename XT, typename ZT, int ADD, int MUL>
+template <typename XT, typename ZT, int ADD, int MUL, bool SPARSE>
 __global__ void __launch_bounds__(256) spmv_run_kernel(const RunArgs p) {
     const int64_t run = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (run >= p.nruns) return;
-    spmv_run_body<XT, ZT, ADD, MUL, false>(p, run, threadIdx.x & 31, nullptr, 0u);
+    spmv_run_body<XT, ZT, ADD, MUL, false, SPARSE>(p, run, threadIdx.x & 31, nullptr, 0u);
 }
 
 template <typename XT, typename ZT, int ADD, int MUL, int THREADS, int MINB>
@@ -511,7 +521,7 @@ __global__ void __launch_bounds__(THREADS, MINB) spmv_run_hot_kernel(const RunAr
 
 // rows that continue past their run: tail partial (+) head partials of the following runs, 8 lanes per open row.
 // Every run after `run` up to tail_last starts inside that row, so its head partial exists.
-template <typename ZT, int ADD_C>
+template <typename ZT, int ADD_C, bool SPARSE>
 __global__ void __launch_bounds__(256) spmv_run_fixup_kernel(const RunArgs p) {
     const int ADD = ADD_C >= 0 ? ADD_C : p.add_op;
     const int sub = threadIdx.x & 7;
@@ -520,9 +530,9 @@ __global__ void __launch_bounds__(256) spmv_run_fixup_kernel(const RunArgs p) {
     Part<ZT> acc{(ZT)0, 0};
     if (r >= 0) {
         const int64_t last_run = __ldg(p.tail_last + run);
-        if (sub == 0) { acc.v = static_cast<const ZT *>(p.tail_val)[run]; acc.has = 1; }
+        if (sub == 0) { acc.v = static_cast<const ZT *>(p.tail_val)[run]; acc.has = SPARSE ? (int)p.tail_has[run] : 1; }
         for (int64_t t = run + 1 + sub; t <= last_run; t += 8) {
-            const Part<ZT> y{static_cast<const ZT *>(p.head_val)[t], 1};
+            const Part<ZT> y{static_cast<const ZT *>(p.head_val)[t], SPARSE ? (int)p.head_has[t] : 1};
             acc = part_join<ZT>(ADD, acc, y);
         }
     }
@@ -531,7 +541,7 @@ __global__ void __launch_bounds__(256) spmv_run_fixup_kernel(const RunArgs p) {
         Part<ZT> y; y.v = shfl_xor_t<ZT>(acc.v, o); y.has = __shfl_xor_sync(0xffffffffu, acc.has, o);
         acc = part_join<ZT>(ADD, acc, y);
     }
-    if (r >= 0 && sub == 0) static_cast<ZT *>(p.tval)[r] = acc.v;
+    if (r >= 0 && sub == 0) { static_cast<ZT *>(p.tval)[r] = acc.v; if (SPARSE) p.tpres[r] = (uint8_t)acc.has; }
 }
 
 // ---- run plan (cached per CSR)
@@ -614,7 +624,7 @@ static GrB_Info spmv_run_plan(Csr &c, std::string *err) {
 
 template <typename XT, typename ZT, int ADD, int MUL>
 static void spmv_run_launch(const RunArgs &a, size_t hot_bytes, int64_t hused) {
-    if (hot_bytes && ADD >= 0) {
+    if (hot_bytes && ADD >= 0 && !a.upres) {
         // two shapes: one 1024-thread CTA per SM with a table of up to ~200 KB, or two 768-thread CTAs
         // per SM (<= 42 registers) with a table of up to ~100 KB each
         const bool two = hot_bytes <= ((size_t)104 << 10) && getenv("B200GRB_HOT_ONE") == nullptr;
@@ -629,10 +639,14 @@ static void spmv_run_launch(const RunArgs &a, size_t hot_bytes, int64_t hused) {
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             kernel<<<G.num_sms, 1024, smem, G.stream>>>(a, hot_n); GB_LAUNCHED();
         }
+    } else if (a.upres) {
+        spmv_run_kernel<XT, ZT, ADD, MUL, true><<<(unsigned)ceil_div(a.nruns, 8), 256, 0, G.stream>>>(a); GB_LAUNCHED();
+        spmv_run_fixup_kernel<ZT, ADD, true><<<(unsigned)ceil_div(a.nruns * 8, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED();
+        return;
     } else {
-        spmv_run_kernel<XT, ZT, ADD, MUL><<<(unsigned)ceil_div(a.nruns, 8), 256, 0, G.stream>>>(a); GB_LAUNCHED();
+        spmv_run_kernel<XT, ZT, ADD, MUL, false><<<(unsigned)ceil_div(a.nruns, 8), 256, 0, G.stream>>>(a); GB_LAUNCHED();
     }
-    spmv_run_fixup_kernel<ZT, ADD><<<(unsigned)ceil_div(a.nruns * 8, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED();
+    spmv_run_fixup_kernel<ZT, ADD, false><<<(unsigned)ceil_div(a.nruns * 8, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED();
 }
 
 template <typename T> static bool spmv_run_fast(int add, int mul, const RunArgs &a, size_t hot_bytes, int64_t hused) {
@@ -1092,7 +1106,7 @@ __global__ void vec_finalize_kernel(const VecFinalizeArgs a) {
             } else if (tp) { out = sc_cast(sc_load(a.ttc, a.tval, i), a.ttc, a.wtc); op = true; }
         } else if (!a.replace && wp) { out = sc_load(a.wtc, a.wval, i); op = true; }
         if (op) sc_store(a.wtc, a.oval, i, out);
-        a.opres[i] = op;
+        if (a.opres) a.opres[i] = op;
     }
 }
 
@@ -1139,7 +1153,8 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
     const bool need_a = kflip ? op_uses_y(kmul) : op_uses_x(kmul);
     const bool need_u = kflip ? op_uses_x(kmul) : op_uses_y(kmul);
     const bool sparse_u = u->dpres != nullptr;
-    const bool fast = !kflip && spmv_is_fast(xt, zt, add, kmul, sparse_u);
+    const bool fast_sr = !kflip && spmv_is_fast(xt, zt, add, kmul, false);      // a compile-time specialised semiring
+    const bool fast = fast_sr && !sparse_u;
     { const char *e = getenv("B200GRB_SPMV_ITEMS"); const int v = e ? atoi(e) : 8; g_items_fast = (v == 16 || v == 4) ? v : 8; }
     const int tile = SPMV_THREADS * (fast ? g_items_fast : g_items_generic);
     GB_TRY(spmv_plan(c, tile, err));
@@ -1178,7 +1193,7 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
         if (r != GrB_SUCCESS) { dfree(tval); dfree(tpres); dfree(a_cast); dfree(u_cast); return r; }
     }
     // dense u + specialised semiring: warp-independent run kernel on the cached run plan
-    const bool run_ok = !use_pull && !sparse_u && (fast || xt == zt || zt == TC_BOOL);     // dense u: specialised or run-time operators
+    const bool run_ok = !use_pull && (fast_sr || xt == zt || zt == TC_BOOL);     // specialised or run-time operators; dense or sparse u
     bool use_run = run_ok && c.nnz >= 4096;
     if (const char *e = getenv("B200GRB_SPMV_RUN")) use_run = run_ok && c.nnz > 0 && atoi(e) != 0;
     if (use_pull) {
@@ -1186,7 +1201,8 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
     } else if (use_run) {
         GB_TRY(spmv_run_plan(c, err));
         CU_TRY(cudaMemsetAsync(tval, 0, (size_t)n * zsz, G.stream), err);
-        CU_TRY(cudaMemcpyAsync(tpres, c.pres_tmpl, (size_t)n, cudaMemcpyDeviceToDevice, G.stream), err);
+        if (sparse_u) CU_TRY(cudaMemsetAsync(tpres, 0, (size_t)n, G.stream), err);     // presence follows u: written row by row
+        else CU_TRY(cudaMemcpyAsync(tpres, c.pres_tmpl, (size_t)n, cudaMemcpyDeviceToDevice, G.stream), err);
         RunArgs ra{};
         ra.col = c.col; ra.aval = aval; ra.uval = uval; ra.headw = c.run_headw; ra.lane_rank = c.run_lane; ra.run_base = c.run_base;
         ra.nzrow = c.nzrow; ra.rowptr = c.rowptr32; ra.nruns = c.nruns; ra.nnz = c.nnz; ra.tval = tval;
@@ -1194,6 +1210,11 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
         ra.add_op = add; ra.mul_op = kmul; ra.flip = kflip;
         GB_TRY(dmalloc(&ra.head_val, (size_t)c.nruns * zsz + 16, err));
         GB_TRY(dmalloc(&ra.tail_val, (size_t)c.nruns * zsz + 16, err));
+        if (sparse_u) {
+            ra.upres = u->dpres; ra.tpres = tpres;
+            GB_TRY(dmalloc((void **)&ra.head_has, (size_t)c.nruns + 16, err));
+            GB_TRY(dmalloc((void **)&ra.tail_has, (size_t)c.nruns + 16, err));
+        }
         void *u_perm = nullptr; size_t hot_bytes = 0;
         // hot-column table: on by default for large matrices whose gathers are concentrated (R-MAT-like);
         // B200GRB_SPMV_HOT=0 disables it, =<KB> forces a table size
@@ -1209,8 +1230,8 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
             if (c.hused > 0) { permute_u_kernel<<<hgrid(c.hused), 256, 0, G.stream>>>(c.hperm, (const uint8_t *)uval, (uint8_t *)u_perm, (int)xsz, c.hused); GB_LAUNCHED(); }
             ra.col = c.hcol; ra.uval = u_perm; hot_bytes = (size_t)hot_kb << 10;
         }
-        const bool ok = fast ? spmv_run_dispatch(xt, add, kmul, ra, hot_bytes, c.hused) : spmv_run_generic(xt, zt, ra);
-        dfree(u_perm); dfree(ra.head_val); dfree(ra.tail_val);
+        const bool ok = fast_sr ? spmv_run_dispatch(xt, add, kmul, ra, hot_bytes, c.hused) : spmv_run_generic(xt, zt, ra);
+        dfree(u_perm); dfree(ra.head_val); dfree(ra.tail_val); dfree(ra.head_has); dfree(ra.tail_has);
         if (!ok) { dfree(tval); dfree(tpres); dfree(a_cast); dfree(u_cast); return gb_fail(GrB_PANIC, err, "mxv: internal dispatch error"); }
     } else if (c.nnz == 0) {
         clear_presence_kernel<<<grid_for(n), 256, 0, G.stream>>>(tpres, n); GB_LAUNCHED();
@@ -1272,7 +1293,10 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
         fa.accum_op = accum ? accum->opcode : -1;
         fa.accum_tc = accum ? accum->xtype->code : 0; fa.accum_ztc = accum ? accum->ztype->code : 0;
         GB_TRY(dmalloc(&fa.oval, (size_t)n * tc_size(wtc) + 16, err));
-        GB_TRY(dmalloc((void **)&fa.opres, (size_t)n + 16, err));
+        // a full w stays full under an accumulator (and a mask that does not replace): no presence bytes, and
+        // the next sweep sees a dense operand (SSSP: v = min(v, A' min.+ v))
+        const bool out_full = !w_empty && w->dpres == nullptr && accum != nullptr && !(mask && f.replace);
+        if (!out_full) GB_TRY(dmalloc((void **)&fa.opres, (size_t)n + 16, err));
         vec_finalize_kernel<<<grid_for(n), 256, 0, G.stream>>>(fa); GB_LAUNCHED();
         dfree(tval); dfree(tpres);
         vector_adopt_device(w, fa.oval, fa.opres);

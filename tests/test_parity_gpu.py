@@ -322,6 +322,37 @@ def _large_spmv_body():
             assert np.array_equal(x[p != 0], ref.X), name      # small integers: exact in every type
 
 
+@pytest.mark.parametrize("dens", [0.0005, 0.03, 0.6])
+def test_large_spmv_sparse_u(dens):
+    """Sparse u on a large matrix (run kernel with presence bytes), specialised and run-time semirings, mxv and
+    vxm, with and without accumulator; exact against the oracle on small-integer data."""
+    n, indptr, indices = _rmat(16)
+    rng = np.random.default_rng(12)
+    rows = np.repeat(np.arange(n), np.diff(indptr))
+    for typ, sr_names in ((FP32, ["PLUS_TIMES", "MIN_PLUS", "MAX_SECOND"]), (INT64, ["PLUS_PAIR", "MIN_FIRST", "TIMES_MAX"]), (BOOL, ["LOR_LAND", "LXOR_LOR"])):
+        vals = rng.integers(1, 4, len(indices)).astype(typ.dtype)
+        ui = np.sort(rng.choice(n, max(1, int(n * dens)), replace=False))
+        ux = rng.integers(0, 3, len(ui)).astype(typ.dtype)
+        A = Matrix.from_csr(indptr, indices, vals, n, n, typ)
+        oA = orc.SpMat(typ.name, n, n, rows, indices, vals)
+        for k, name in enumerate(sr_names):
+            add, mul = name.split("_")
+            u = Vector.from_lists(ui.tolist(), ux.tolist(), n, typ)
+            ou = orc.SpVec(typ.name, n, ui, ux)
+            if k % 2 == 0:
+                w = A.mxv(u, semiring=getattr(typ, name))
+                ref = orc.mxv(orc.SpVec(typ.name, n), None, None, (add, mul, typ.name), oA, ou)
+            else:
+                w0i = np.sort(rng.choice(n, n // 3, replace=False)); w0x = rng.integers(0, 5, len(w0i)).astype(typ.dtype)
+                w = Vector.from_lists(w0i.tolist(), w0x.tolist(), n, typ)
+                acc = "LOR" if typ is BOOL else "PLUS"
+                u.vxm(A, out=w, accum=getattr(typ, acc), semiring=getattr(typ, name))
+                ref = orc.vxm(orc.SpVec(typ.name, n, w0i, w0x), None, (acc, typ.name), (add, mul, typ.name), ou, oA)
+            I, X = w.to_arrays()
+            assert np.array_equal(I, ref.I), (name, dens)
+            assert np.array_equal(X, ref.X), (name, dens)
+
+
 def test_rmat_unmasked_spgemm_matches_scipy():
     """configs[3] secondary: unmasked A (+.second) A, all three row bins (hash / hash / dense accumulator)."""
     n, indptr, indices = _rmat(12)
