@@ -1,0 +1,33 @@
+// Argument blocks of the run and pull kernels (host side fills them in spmv.cu).
+#pragma once
+#include "spmv_common.cuh"
+
+static constexpr int RUN = 256;
+struct RunArgs {
+    const uint32_t *col; const void *aval; const void *uval;
+    const uint32_t *headw; const uint16_t *lane_rank; const uint32_t *run_base; const uint32_t *nzrow; const uint32_t *rowptr;
+    const int32_t *tail_row; const uint32_t *tail_last;       // structural: which row is open at a run's end, how far it reaches
+    int64_t nruns; int64_t nnz;
+    void *tval;
+    void *head_val; void *tail_val;                            // per run: partial of the row it starts inside / of the row open at its end
+    int add_op, mul_op, flip;                                  // run-time operator codes (kernels instantiated with ADD = MUL = -1)
+    const uint8_t *upres;                                      // SPARSE kernels: presence bytes of u ...
+    uint8_t *tpres; uint8_t *head_has; uint8_t *tail_has;      // ... and of everything they produce
+};
+
+// ------------------------------------------------------------------ masked pull with early exit (BFS-shaped calls)
+// w<mask> = A (+).(x) u for monoids with a terminal value (LOR, LAND, ANY): one warp per row, rows the mask
+// rules out are skipped entirely (their entries are never read), and a row stops as soon as its monoid
+// saturates -- the BFS step `A.mxv(q, mask=visited, desc=RC, semiring=LOR_LAND)` of
+// /root/reference/tests/test_descriptor.py:13-30 touches only the unvisited rows and, for each, only the
+// entries up to the first frontier hit.  Output: T restricted to the rows the mask lets through.
+struct PullArgs {
+    const uint32_t *rowptr; const uint32_t *col; const void *aval; int64_t nrows;
+    const void *uval; const uint8_t *upres;
+    const void *mval; const uint8_t *mpres; int mtc; int mask_comp, mask_struct;
+    void *tval; uint8_t *tpres;
+    int add_op, mul_op, flip;
+    int has_long; int64_t long_cap;
+    uint32_t *long_rows; int *long_count;                      // work list of the rows left to the CTA-per-row kernel
+};
+constexpr uint32_t PULL_LONG = 4096;          // rows longer than this go to the CTA-per-row kernel
