@@ -63,6 +63,23 @@ def binop(op, typ, x, y):
             return dt(y - x)
         if op == "TIMES":
             return dt(x * y)
+        if op in ("DIV", "RDIV"):
+            a, b = (x, y) if op == "DIV" else (y, x)
+            if np.dtype(dt).kind == "f":
+                return dt(a / b)
+            info = np.iinfo(dt)                      # GraphBLAS integer division: x/0 and INT_MIN/-1 are defined
+            if b == 0:
+                return dt(0) if a == 0 else dt(info.min if a < 0 else info.max)
+            if np.dtype(dt).kind == "i" and b == -1:
+                return dt(0) - a
+            q = abs(int(a)) // abs(int(b))
+            return dt(q if (int(a) < 0) == (int(b) < 0) else -q)
+        if op == "BOR":
+            return dt(x | y)
+        if op == "BAND":
+            return dt(x & y)
+        if op == "BXOR":
+            return dt(x ^ y)
         if op == "LOR":
             return dt((x != 0) or (y != 0))
         if op == "LAND":

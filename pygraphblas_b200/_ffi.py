@@ -54,6 +54,14 @@ def declared_symbols():
 ffi = FFI()
 ffi.cdef(header_cdef())
 
+if not os.path.exists(LIB_PATH) or os.environ.get("B200GRB_BUILD"):
+    # first import of a fresh checkout (or B200GRB_BUILD=1 after editing the sources): compile in-tree with nvcc
+    try:
+        from .build import build_library
+        build_library(verbose=bool(os.environ.get("B200GRB_BUILD")))
+    except Exception as e:                                   # no nvcc on this machine
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing and could not be built: {e}")
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} is missing: build it with `python -m pygraphblas_b200.build` "

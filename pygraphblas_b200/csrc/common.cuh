@@ -46,7 +46,16 @@ struct GB_Descriptor_opaque {
     int magic; int outp, mask, inp0, inp1; int axb; int nthreads; double chunk; int sort;
     bool builtin; const char *name;
 };
-struct GB_UnaryOp_opaque { int magic; };
+struct GB_UnaryOp_opaque { int magic; int opcode; GrB_Type xtype, ztype; const char *name; };
+enum UnaryCode : int {
+    UOP_IDENTITY = 0, UOP_AINV, UOP_MINV, UOP_LNOT, UOP_ONE, UOP_ABS, UOP_BNOT,
+    // floating point only
+    UOP_SQRT, UOP_LOG, UOP_EXP, UOP_LOG2, UOP_SIN, UOP_COS, UOP_TAN, UOP_ACOS, UOP_ASIN, UOP_ATAN, UOP_SINH, UOP_COSH,
+    UOP_TANH, UOP_ACOSH, UOP_ASINH, UOP_ATANH, UOP_SIGNUM, UOP_CEIL, UOP_FLOOR, UOP_ROUND, UOP_TRUNC, UOP_EXP2,
+    UOP_EXPM1, UOP_LOG10, UOP_LOG1P, UOP_LGAMMA, UOP_TGAMMA, UOP_ERF, UOP_ERFC,
+    UOP_ISINF, UOP_ISNAN, UOP_ISFINITE,      // z = BOOL
+    UOP_COUNT
+};
 
 // Device CSR panel: rows sorted, columns sorted inside each row.
 struct Csr {
@@ -145,6 +154,13 @@ bool gb_valid_vector(const GrB_Vector v);
 struct DescFlags { bool replace, mask_comp, mask_struct, tran0, tran1; int axb; };
 DescFlags desc_flags(const GrB_Descriptor d);
 
+// w<mask> = accum(w, T) on the device (vector_ops.cu).  T = (tval, tpres) of type ttc over w->n positions
+// (tpres NULL: every position present; t_scalar: tval is ONE value standing for all positions).  region
+// (NULL = everything) limits the write to the positions it flags, GrB_assign style.  own_t: T's buffers are
+// released here.
+GrB_Info vector_write(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const DescFlags &f,
+                      void *tval, uint8_t *tpres, int ttc, bool t_scalar, const uint8_t *region, bool own_t);
+
 // kernels (device_ops.cu / spmv.cu / spgemm.cu)
 GrB_Info dev_build_rowptr32(Csr &c, std::string *err);
 GrB_Info dev_exclusive_scan(int64_t *data, int64_t n, std::string *err);
@@ -156,6 +172,7 @@ GrB_Info dev_count_present(const uint8_t *pres, int64_t n, int64_t *count, std::
 // A value of any builtin type held in 64 bits: BOOL/UINT* in .u, INT* in .i, FP* in .d
 // (a float is held as the exactly-equal double).
 struct Sc { union { int64_t i; uint64_t u; double d; }; };
+struct GB_Scalar_opaque { int magic; GrB_Type type; bool has; Sc v; };     // GxB_Scalar (compat.cu)
 
 __host__ __device__ static inline int tc_size(int tc) {
     switch (tc) {
@@ -455,6 +472,72 @@ __host__ __device__ static inline Sc sc_binop(int op, int tc, Sc x, Sc y) {
     }
 #undef GB_CASE
     return r;
+}
+
+// carrier-level unary operator: x of type `tc`; z of type `tc` (BOOL for ISINF / ISNAN / ISFINITE)
+template <typename T> __host__ __device__ static inline T uop_apply(int op, T x) {
+    typedef typename UnsignedOf<T>::type U;
+    constexpr bool F = NumTraits<T>::is_float;
+    switch (op) {
+        case UOP_IDENTITY: return x;
+        case UOP_AINV: if (F) return -x; return (T)((U)0 - (U)x);
+        case UOP_MINV: if constexpr (F) return (T)1 / x; else return int_div<T>((T)1, x);
+        case UOP_LNOT: return (T)!(x != (T)0);
+        case UOP_ONE:  return (T)1;
+        case UOP_ABS:  if constexpr (F) return (T)fabs((double)x); else if constexpr (NumTraits<T>::is_signed) return x < 0 ? (T)((U)0 - (U)x) : x; else return x;
+        case UOP_BNOT: if constexpr (F) return x; else return (T)~(U)x;
+        default: break;
+    }
+    if constexpr (F) {
+        const double d = (double)x;
+        switch (op) {
+            case UOP_SQRT: return (T)sqrt(d);   case UOP_LOG: return (T)log(d);     case UOP_EXP: return (T)exp(d);
+            case UOP_LOG2: return (T)log2(d);   case UOP_SIN: return (T)sin(d);     case UOP_COS: return (T)cos(d);
+            case UOP_TAN: return (T)tan(d);     case UOP_ACOS: return (T)acos(d);   case UOP_ASIN: return (T)asin(d);
+            case UOP_ATAN: return (T)atan(d);   case UOP_SINH: return (T)sinh(d);   case UOP_COSH: return (T)cosh(d);
+            case UOP_TANH: return (T)tanh(d);   case UOP_ACOSH: return (T)acosh(d); case UOP_ASINH: return (T)asinh(d);
+            case UOP_ATANH: return (T)atanh(d); case UOP_SIGNUM: return (T)(d != d ? d : (d > 0) - (d < 0));
+            case UOP_CEIL: return (T)ceil(d);   case UOP_FLOOR: return (T)floor(d); case UOP_ROUND: return (T)round(d);
+            case UOP_TRUNC: return (T)trunc(d); case UOP_EXP2: return (T)exp2(d);   case UOP_EXPM1: return (T)expm1(d);
+            case UOP_LOG10: return (T)log10(d); case UOP_LOG1P: return (T)log1p(d); case UOP_LGAMMA: return (T)lgamma(d);
+            case UOP_TGAMMA: return (T)tgamma(d); case UOP_ERF: return (T)erf(d);   case UOP_ERFC: return (T)erfc(d);
+            default: break;
+        }
+    }
+    return x;
+}
+__host__ __device__ static inline Sc sc_unop(int op, int tc, Sc x) {
+    Sc r; r.u = 0;
+    if (op >= UOP_ISINF && op <= UOP_ISFINITE) {
+        const double d = tc == TC_FP32 ? (double)(float)x.d : x.d;
+        const bool inf = d == (double)INFINITY || d == -(double)INFINITY, nan = d != d;
+        r.u = op == UOP_ISINF ? inf : (op == UOP_ISNAN ? nan : (!inf && !nan));
+        return r;
+    }
+#define GB_CASE(TC, T, FIELD) case TC: { Sc t; t.u = 0; t.FIELD = uop_apply<T>(op, (T)x.FIELD); r = t; } break;
+    switch (tc) {
+        case TC_BOOL: r.u = uop_apply<bool>(op, x.u != 0); break;
+        GB_CASE(TC_INT8, int8_t, i) GB_CASE(TC_INT16, int16_t, i) GB_CASE(TC_INT32, int32_t, i) GB_CASE(TC_INT64, int64_t, i)
+        GB_CASE(TC_UINT8, uint8_t, u) GB_CASE(TC_UINT16, uint16_t, u) GB_CASE(TC_UINT32, uint32_t, u) GB_CASE(TC_UINT64, uint64_t, u)
+        case TC_FP32: r.d = (double)uop_apply<float>(op, (float)x.d); break;
+        case TC_FP64: r.d = uop_apply<double>(op, x.d); break;
+    }
+#undef GB_CASE
+    return r;
+}
+// identity of a builtin monoid operator, on the carrier (same table the kernels use)
+__host__ __device__ static inline Sc sc_monoid_identity(int op, int tc) {
+    Sc acc; acc.u = 0;
+    switch (tc) {
+#define GB_ID(TC, T, F) case TC: { Sc t; t.u = 0; t.F = monoid_identity<T>(op); acc = t; } break;
+        case TC_BOOL: acc.u = monoid_identity<bool>(op); break;
+        GB_ID(TC_INT8, int8_t, i) GB_ID(TC_INT16, int16_t, i) GB_ID(TC_INT32, int32_t, i) GB_ID(TC_INT64, int64_t, i)
+        GB_ID(TC_UINT8, uint8_t, u) GB_ID(TC_UINT16, uint16_t, u) GB_ID(TC_UINT32, uint32_t, u) GB_ID(TC_UINT64, uint64_t, u)
+        case TC_FP32: acc.d = (double)monoid_identity<float>(op); break;
+        case TC_FP64: acc.d = monoid_identity<double>(op); break;
+#undef GB_ID
+    }
+    return acc;
 }
 
 // ---------------------------------------------------------------- launch helpers

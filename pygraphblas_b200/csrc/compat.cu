@@ -11,7 +11,6 @@
 #include <algorithm>
 #include "../../include/b200grb_compat.h"
 
-struct GB_Scalar_opaque { int magic; GrB_Type type; bool has; Sc v; };
 struct GB_SelectOp_opaque { int magic; const char *name; };
 
 static GB_Type_opaque type_FC32 = {GB_MAGIC, TC_COUNT, 8, "FC32"};
@@ -120,7 +119,7 @@ static GrB_Info matrix_reduce(void *c, int ctc, const GrB_BinaryOp accum, const 
     GB_TRY(matrix_ensure_host(A));
     return reduce_values(c, ctc, accum, monoid, A->type->code, A->hx, A->hi.size(), "GrB_Matrix_reduce");
 }
-static GrB_Info vector_reduce(void *c, int ctc, const GrB_BinaryOp accum, const GrB_Monoid monoid, const GrB_Vector u) {
+GrB_Info host_vector_reduce(void *c, int ctc, const GrB_BinaryOp accum, const GrB_Monoid monoid, const GrB_Vector u) {
     GB_LOCK;
     if (!gb_valid_vector(u)) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "GrB_Vector_reduce: invalid vector");
     GB_TRY(vector_ensure_host(u));
@@ -129,8 +128,7 @@ static GrB_Info vector_reduce(void *c, int ctc, const GrB_BinaryOp accum, const 
 #define GB_COMPAT_TYPED(TN, CT, TC) \
     extern "C" GrB_Info GxB_Scalar_setElement_##TN(GxB_Scalar s, CT x) { return scalar_set(s, TC, &x); } \
     extern "C" GrB_Info GxB_Scalar_extractElement_##TN(CT *x, const GxB_Scalar s) { return scalar_get(x, TC, s); } \
-    extern "C" GrB_Info GrB_Matrix_reduce_##TN(CT *c, const GrB_BinaryOp accum, const GrB_Monoid m, const GrB_Matrix A, const GrB_Descriptor d) { (void)d; return matrix_reduce(c, TC, accum, m, A); } \
-    extern "C" GrB_Info GrB_Vector_reduce_##TN(CT *c, const GrB_BinaryOp accum, const GrB_Monoid m, const GrB_Vector u, const GrB_Descriptor d) { (void)d; return vector_reduce(c, TC, accum, m, u); }
+    extern "C" GrB_Info GrB_Matrix_reduce_##TN(CT *c, const GrB_BinaryOp accum, const GrB_Monoid m, const GrB_Matrix A, const GrB_Descriptor d) { (void)d; return matrix_reduce(c, TC, accum, m, A); }
 GB_COMPAT_TYPED(BOOL, bool, TC_BOOL) GB_COMPAT_TYPED(INT8, int8_t, TC_INT8) GB_COMPAT_TYPED(INT16, int16_t, TC_INT16) GB_COMPAT_TYPED(INT32, int32_t, TC_INT32)
 GB_COMPAT_TYPED(INT64, int64_t, TC_INT64) GB_COMPAT_TYPED(UINT8, uint8_t, TC_UINT8) GB_COMPAT_TYPED(UINT16, uint16_t, TC_UINT16)
 GB_COMPAT_TYPED(UINT32, uint32_t, TC_UINT32) GB_COMPAT_TYPED(UINT64, uint64_t, TC_UINT64) GB_COMPAT_TYPED(FP32, float, TC_FP32) GB_COMPAT_TYPED(FP64, double, TC_FP64)
@@ -171,8 +169,9 @@ extern "C" GrB_Info GrB_Matrix_eWiseMult_BinaryOp(GrB_Matrix C, const GrB_Matrix
     C->hi.swap(ri); C->hj.swap(rj); C->hx.swap(rx); C->pi.clear(); C->pj.clear(); C->px.clear(); C->host_valid = true;
     return GrB_SUCCESS;
 }
-extern "C" GrB_Info GrB_Vector_eWiseMult_BinaryOp(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_BinaryOp op,
-                                                   const GrB_Vector u, const GrB_Vector v, const GrB_Descriptor desc) {
+// (with a CUDA device present the vector form runs on the GPU: vector_ops.cu)
+GrB_Info host_vector_emult(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_BinaryOp op,
+                           const GrB_Vector u, const GrB_Vector v, const GrB_Descriptor desc) {
     GB_LOCK;
     if (!gb_valid_vector(w) || !gb_valid_vector(u) || !gb_valid_vector(v)) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "GrB_Vector_eWiseMult_BinaryOp: invalid vector");
     GB_TRY(emult_check(mask, accum, op, desc, "GrB_Vector_eWiseMult_BinaryOp"));

@@ -433,41 +433,6 @@ static GrB_Info spmv_dispatch(int xt, int zt, int add, int mul, bool sparse_u, c
     return gb_fail(GrB_DOMAIN_MISMATCH, err, "mxv: unsupported semiring domains (x=%d, z=%d)", xt, zt);
 }
 
-// ------------------------------------------------------------------ finalize:  w<mask> = accum(w, t)
-struct VecFinalizeArgs {
-    int64_t n;
-    const void *wval; const uint8_t *wpres; int wtc; int w_exists;
-    const void *tval; const uint8_t *tpres; int ttc;
-    const void *mval; const uint8_t *mpres; int mtc; int has_mask, mask_comp, mask_struct, replace;
-    int accum_op, accum_tc, accum_ztc;   // accum_op < 0: none
-    void *oval; uint8_t *opres;
-};
-__global__ void vec_finalize_kernel(const VecFinalizeArgs a) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
-        const bool tp = a.tpres ? a.tpres[i] != 0 : true;
-        const bool wp = a.w_exists ? (a.wpres ? a.wpres[i] != 0 : true) : false;
-        bool m = true;
-        if (a.has_mask) {
-            m = a.mpres ? a.mpres[i] != 0 : true;
-            if (m && !a.mask_struct) { const Sc mv = sc_cast(sc_load(a.mtc, a.mval, i), a.mtc, TC_BOOL); m = mv.u != 0; }
-            if (a.mask_comp) m = !m;
-        }
-        Sc out; out.u = 0; bool op = false;
-        if (m) {
-            if (a.accum_op >= 0) {
-                if (wp && tp) {
-                    const Sc x = sc_cast(sc_load(a.wtc, a.wval, i), a.wtc, a.accum_tc);
-                    const Sc y = sc_cast(sc_load(a.ttc, a.tval, i), a.ttc, a.accum_tc);
-                    out = sc_cast(sc_binop(a.accum_op, a.accum_tc, x, y), a.accum_ztc, a.wtc); op = true;
-                } else if (wp) { out = sc_load(a.wtc, a.wval, i); op = true; }
-                else if (tp) { out = sc_cast(sc_load(a.ttc, a.tval, i), a.ttc, a.wtc); op = true; }
-            } else if (tp) { out = sc_cast(sc_load(a.ttc, a.tval, i), a.ttc, a.wtc); op = true; }
-        } else if (!a.replace && wp) { out = sc_load(a.wtc, a.wval, i); op = true; }
-        if (op) sc_store(a.wtc, a.oval, i, out);
-        if (a.opres) a.opres[i] = op;
-    }
-}
-
 static inline int grid_for(int64_t n, int threads = 256) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, threads), (int64_t)G.num_sms * 16));
 }
@@ -632,35 +597,8 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
     }
     dfree(a_cast); dfree(u_cast);
 
-    // ---- w<mask> = accum(w, t)
-    const int wtc = w->type->code;
-    if (!need_final) {
-        if (wtc == zt) vector_adopt_device(w, tval, tpres);
-        else {
-            void *cv = nullptr;
-            GB_TRY(dev_cast_values(&cv, wtc, tval, zt, n, err));
-            dfree(tval);
-            vector_adopt_device(w, cv, tpres);
-        }
-    } else {
-        VecFinalizeArgs fa{};
-        fa.n = n; fa.wval = w->dval; fa.wpres = w->dpres; fa.wtc = wtc; fa.w_exists = w_empty ? 0 : 1;
-        fa.tval = tval; fa.tpres = tpres; fa.ttc = zt;
-        if (mask) { fa.mval = mask->dval; fa.mpres = mask->dpres; fa.mtc = mask->type->code; fa.has_mask = 1; }
-        fa.mask_comp = f.mask_comp; fa.mask_struct = f.mask_struct; fa.replace = f.replace;
-        fa.accum_op = accum ? accum->opcode : -1;
-        fa.accum_tc = accum ? accum->xtype->code : 0; fa.accum_ztc = accum ? accum->ztype->code : 0;
-        GB_TRY(dmalloc(&fa.oval, (size_t)n * tc_size(wtc) + 16, err));
-        // a full w stays full under an accumulator (and a mask that does not replace): no presence bytes, and
-        // the next sweep sees a dense operand (SSSP: v = min(v, A' min.+ v))
-        const bool out_full = !w_empty && w->dpres == nullptr && accum != nullptr && !(mask && f.replace);
-        if (!out_full) GB_TRY(dmalloc((void **)&fa.opres, (size_t)n + 16, err));
-        vec_finalize_kernel<<<grid_for(n), 256, 0, G.stream>>>(fa); GB_LAUNCHED();
-        dfree(tval); dfree(tpres);
-        vector_adopt_device(w, fa.oval, fa.opres);
-    }
-    CU_TRY(cudaGetLastError(), err);
-    return GrB_SUCCESS;
+    // ---- w<mask> = accum(w, t)   (vector_ops.cu)
+    return vector_write(w, mask, accum, f, tval, tpres, zt, /*t_scalar=*/false, /*region=*/nullptr, /*own_t=*/true);
 }
 
 static GrB_Info mxv_check(GrB_Vector w, const GrB_Vector mask, const GrB_Semiring s, const GrB_Matrix A, const GrB_Vector u, const char *fn) {

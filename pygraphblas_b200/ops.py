@@ -28,6 +28,23 @@ class BinaryOp:
         return f"<BinaryOp {self.name}>"
 
 
+class UnaryOp:
+    """Builtin unary operator (unaryop.py:21-50): `FP32.ABS(v)` = `v.apply(FP32.ABS)`."""
+
+    def __init__(self, op, typ, handle):
+        self.op, self.type, self.unaryop = op, typ, handle
+        self.name = f"{op}_{typ}"
+
+    def __call__(self, A, *args, **kwargs):
+        return A.apply(self, *args, **kwargs)
+
+    def get_op(self):
+        return self.unaryop
+
+    def __repr__(self):
+        return f"<UnaryOp {self.name}>"
+
+
 class Accum:
     """`with Accum(INT64.min): o @= n`  (binaryop.py:80-101)."""
 
@@ -101,7 +118,7 @@ _monoid_res = (re.compile(rf"^GxB_([A-Z]+)_({_T})_MONOID$"), re.compile(rf"^GrB_
 _semiring_re = re.compile(rf"^(?:GrB|GxB)_([A-Z]+)_([A-Z]+)_(?:SEMIRING_)?({_T})$")
 _skip_binop_prefix = ("Matrix", "Vector", "Monoid", "DESC", "ONEB")
 
-binaryops, monoids, semirings = {}, {}, {}
+binaryops, monoids, semirings, unaryops = {}, {}, {}, {}
 
 
 def _attach(typ_name, attr, obj):
@@ -121,6 +138,12 @@ def _discover():
             b = BinaryOp(m.group(1), m.group(2), obj)
             binaryops[b.name] = b
             _attach(m.group(2), m.group(1), b)
+    for n in names:
+        m = _binop_re.match(n)
+        if m and ffi.typeof(getattr(lib, n)).cname == "struct GB_UnaryOp_opaque *":
+            u = UnaryOp(m.group(1), m.group(2), getattr(lib, n))
+            unaryops[u.name] = u
+            _attach(m.group(2), m.group(1), u)
     for n in names:
         for r in _monoid_res:
             m = r.match(n)

@@ -29,6 +29,16 @@ class Type:
         self._Vector_extractElement = fn("Vector_extractElement")
         self._Vector_extractTuples = fn("Vector_extractTuples")
         self._Vector_build = fn("Vector_build")
+        self._Vector_assignScalar = fn("Vector_assign")                 # types.py:103 of the reference
+        self._Vector_apply_BinaryOp1st = fn("Vector_apply_BinaryOp1st")
+        self._Vector_apply_BinaryOp2nd = fn("Vector_apply_BinaryOp2nd")
+        self._Vector_reduce = fn("Vector_reduce")
+
+    def _default_addop(self):                                           # types.py:157-160
+        return self.LOR if self is BOOL else self.PLUS
+
+    def _default_multop(self):
+        return self.LAND if self is BOOL else self.TIMES
 
     def __repr__(self):
         return f"<Type {self.name}>"
@@ -58,6 +68,17 @@ _by_handle = {t.gb_type: t for t in ALL_TYPES}
 
 # types.py:468-481
 _promotion_order = (FP64, FP32, INT64, UINT64, INT32, UINT32, INT16, UINT16, INT8, UINT8)
+
+
+def from_python(value):
+    """GraphBLAS type of a Python scalar (types.py:_gb_from_type of the reference: bool, int, float)."""
+    if isinstance(value, (bool, np.bool_)):
+        return BOOL
+    if isinstance(value, (int, np.integer)):
+        return INT64
+    if isinstance(value, (float, np.floating)):
+        return FP64
+    raise TypeError(f"no GraphBLAS type for {type(value).__name__}")
 
 
 def by_name(name):

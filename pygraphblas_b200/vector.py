@@ -151,6 +151,8 @@ class Vector:
         return iter(zip(I, X))
 
     def __getitem__(self, i):
+        if not isinstance(i, (int, np.integer)):
+            return self.extract(i)
         typ = self.type
         x = ffi.new(typ.ptr)
         res = typ._Vector_extractElement(x, self._vector[0], i)
@@ -166,6 +168,14 @@ class Vector:
             return default
 
     def __setitem__(self, i, value):
+        if isinstance(i, Vector):                            # v[mask] = x  (vector.py:1449-1457)
+            if isinstance(value, Vector):
+                return self.assign(value, None, mask=i)
+            return self.assign_scalar(value, None, mask=i)
+        if not isinstance(i, (int, np.integer)):
+            if isinstance(value, Vector):
+                return self.assign(value, i)
+            return self.assign_scalar(value, i)
         typ = self.type
         _check(typ._Vector_setElement(self._vector[0], typ.from_value(value), i))
 
@@ -224,6 +234,192 @@ class Vector:
         mask, accum, desc = self._get_args(mask, accum, desc)
         _check(lib.GrB_vxm(out._vector[0], mask, accum, semiring.get_op(), self._vector[0], other._matrix[0], desc))
         return out
+
+    # ------------------------------------------------------------------ loop glue (vector_ops.cu)
+    def _out_like(self, out, typ=None):
+        return out if out is not None else Vector.sparse(typ or self.type, self.size)
+
+    def eadd(self, other, add_op=None, cast=None, out=None, mask=None, accum=None, desc=None):
+        """Element-wise union w<mask> = accum(w, u (+) v)  (vector.py:604-735 of the reference; also `|`, `+`, `-`)."""
+        from .ops import Monoid, Semiring
+        func = lib.GrB_Vector_eWiseAdd_BinaryOp
+        if isinstance(add_op, Monoid):
+            func = lib.GrB_Vector_eWiseAdd_Monoid
+        elif isinstance(add_op, Semiring):
+            func = lib.GrB_Vector_eWiseAdd_Semiring
+        out = self._out_like(out, cast or types.promote(self.type, other.type))
+        if add_op is None:
+            add_op = out.type._default_addop()
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(func(out._vector[0], mask, accum, add_op.get_op(), self._vector[0], other._vector[0], desc))
+        return out
+
+    def emult(self, other, mult_op=None, cast=None, out=None, mask=None, accum=None, desc=None):
+        """Element-wise intersection w<mask> = accum(w, u (x) v)  (vector.py:737-833; also `&`, `*`, `/`)."""
+        out = self._out_like(out, cast or types.promote(self.type, other.type))
+        if mult_op is None:
+            mult_op = out.type._default_multop()
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(lib.GrB_Vector_eWiseMult_BinaryOp(out._vector[0], mask, accum, mult_op.get_op(), self._vector[0], other._vector[0], desc))
+        return out
+
+    def apply(self, op, out=None, mask=None, accum=None, desc=None):
+        """w<mask> = accum(w, f(u))  (vector.py:1101-1129)."""
+        out = self._out_like(out)
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(lib.GrB_Vector_apply(out._vector[0], mask, accum, op.get_op(), self._vector[0], desc))
+        return out
+
+    def apply_first(self, first, op, out=None, mask=None, accum=None, desc=None):
+        """w = op(first, u)  (vector.py:1131-1153)."""
+        out = self._out_like(out)
+        typ = types.from_python(first)
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(typ._Vector_apply_BinaryOp1st(out._vector[0], mask, accum, op.get_op(), typ.from_value(first), self._vector[0], desc))
+        return out
+
+    def apply_second(self, op, second, out=None, mask=None, accum=None, desc=None):
+        """w = op(u, second)  (vector.py:1155-1178)."""
+        out = self._out_like(out)
+        typ = types.from_python(second)
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(typ._Vector_apply_BinaryOp2nd(out._vector[0], mask, accum, op.get_op(), self._vector[0], typ.from_value(second), desc))
+        return out
+
+    def _index(self, index, dim):
+        """(I, ni, length) of a slice / list / None, exactly as base.py:216-252 (_build_range) of the reference
+        builds it: GrB_ALL, an explicit list, or GxB_RANGE / GxB_STRIDE / GxB_BACKWARDS with an INCLUSIVE stop."""
+        if isinstance(index, (list, tuple, np.ndarray)):
+            idx = [int(i) for i in index]
+            return ffi.new("GrB_Index[]", idx if idx else [0]), len(idx), len(idx)
+        if index is None or index == slice(None, None, None):
+            return lib.GrB_ALL, 0, dim
+        start = 0 if index.start is None else index.start
+        stop = dim - 1 if index.stop is None else index.stop
+        step = index.step
+        if step is None:
+            return ffi.new("GrB_Index[2]", [start, stop]), lib.GxB_RANGE, (stop - start) + 1
+        if step < 0:
+            step = abs(step)
+            size = 0 if start < stop else int((start - stop) / step) + 1
+            return ffi.new("GrB_Index[3]", [start, stop, step]), lib.GxB_BACKWARDS, size
+        size = 0 if (start > stop or step == 0) else int((stop - start) / step) + 1
+        return ffi.new("GrB_Index[3]", [start, stop, step]), lib.GxB_STRIDE, size
+
+    def assign_scalar(self, value, index=None, mask=None, accum=None, desc=None):
+        """w<mask>(I) = accum(w(I), x)  (vector.py:1494-1524)."""
+        typ = types.from_python(value)
+        I, ni, _ = self._index(index, self.size)
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(typ._Vector_assignScalar(self._vector[0], mask, accum, typ.from_value(value), I, ni, desc))
+
+    def assign(self, value, index=None, mask=None, accum=None, desc=None):
+        """w<mask>(I) = accum(w(I), u)  (vector.py:1461-1492)."""
+        I, ni, _ = self._index(index, self.size)
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(lib.GrB_Vector_assign(self._vector[0], mask, accum, value._vector[0], I, ni, desc))
+
+    def extract(self, index=None, out=None, mask=None, accum=None, desc=None):
+        """w<mask> = accum(w, u(I))  (vector.py:1526-1560)."""
+        I, ni, length = self._index(index, self.size)
+        if out is None:
+            out = Vector.sparse(self.type, length)
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(lib.GrB_Vector_extract(out._vector[0], mask, accum, self._vector[0], I, ni, desc))
+        return out
+
+    def _reduce(self, typ, mon, accum=None):
+        if mon is None:
+            mon = getattr(typ, "LOR_MONOID" if typ is types.BOOL else "PLUS_MONOID")
+        x = ffi.new(typ.ptr)
+        mask, accum, desc = self._get_args(None, accum, None)
+        _check(typ._Vector_reduce(x, accum, mon.get_op(), self._vector[0], desc))
+        return typ.from_value(x[0])
+
+    def reduce_bool(self, mon=None, **kw):
+        """(vector.py:533-552)"""
+        return self._reduce(types.BOOL, mon, **kw)
+
+    def reduce_int(self, mon=None, **kw):
+        """(vector.py:554-572)"""
+        return self._reduce(types.INT64, mon, **kw)
+
+    def reduce_float(self, mon=None, **kw):
+        """(vector.py:574-593)"""
+        return self._reduce(types.FP64, mon, **kw)
+
+    def pattern(self, typ=types.BOOL):
+        """(vector.py:1405-1414)"""
+        out = Vector.sparse(typ, self.size)
+        self.apply(typ.ONE, out=out)
+        return out
+
+    def _scalar_or_vector(self, other, vec_fn, op, first=False):
+        if isinstance(other, Vector):
+            return vec_fn(other, op)
+        return self.apply_first(other, op) if first else self.apply_second(op, other)
+
+    def __add__(self, o):
+        return self._scalar_or_vector(o, self.eadd, self.type.PLUS)
+
+    def __radd__(self, o):
+        return self._scalar_or_vector(o, self.eadd, self.type.PLUS, first=True)
+
+    def __sub__(self, o):
+        return self._scalar_or_vector(o, self.eadd, self.type.MINUS)
+
+    def __rsub__(self, o):
+        return self._scalar_or_vector(o, self.eadd, self.type.MINUS, first=True)
+
+    def __mul__(self, o):
+        return self._scalar_or_vector(o, self.emult, self.type.TIMES)
+
+    def __rmul__(self, o):
+        return self._scalar_or_vector(o, self.emult, self.type.TIMES, first=True)
+
+    def __truediv__(self, o):
+        return self._scalar_or_vector(o, self.emult, self.type.DIV)
+
+    def _inplace(self, other, vec_fn, op):
+        if isinstance(other, Vector):
+            return vec_fn(other, op, out=self)
+        return self.apply_second(op, other, out=self)
+
+    def __iadd__(self, o):
+        return self._inplace(o, self.eadd, self.type.PLUS)
+
+    def __isub__(self, o):
+        return self._inplace(o, self.eadd, self.type.MINUS)
+
+    def __imul__(self, o):
+        return self._inplace(o, self.emult, self.type.TIMES)
+
+    def __itruediv__(self, o):
+        return self._inplace(o, self.emult, self.type.DIV)
+
+    def __rtruediv__(self, o):
+        return self.apply_first(o, self.type.DIV)
+
+    def __ior__(self, o):
+        return self.eadd(o, out=self)
+
+    def __iand__(self, o):
+        return self.emult(o, out=self)
+
+    def __invert__(self):
+        return self.apply(self.type.MINV)
+
+    def __or__(self, o):
+        return self.eadd(o)
+
+    def __and__(self, o):
+        return self.emult(o)
+
+    def __neg__(self):
+        return self.apply(self.type.AINV)
+
+    def __abs__(self):
+        return self.apply(self.type.ABS)
 
     def __matmul__(self, other):
         from .matrix import Matrix

@@ -79,6 +79,26 @@ for op, code in [("LOR", "LOR"), ("LAND", "LAND"), ("LXOR", "LXOR"), ("LXNOR", "
 for op, code in [("ANY", "ANY"), ("LOR", "LOR"), ("LAND", "LAND"), ("LXOR", "LXOR"), ("EQ", "EQ")]:
     add_monoid(f"GxB_{op}_BOOL_MONOID", code, "BOOL")
 
+# unary operators (apply): /root/reference/pygraphblas/unaryop.py:57-66 discovers them by regex
+unops = []       # (symbol, opcode, xtype, ztype)
+for t in ALL:
+    for op in ["IDENTITY", "AINV", "MINV"]:
+        unops.append((f"GrB_{op}_{t}", op, t, t))
+    for op in ["LNOT", "ONE", "ABS"]:
+        unops.append((f"GxB_{op}_{t}", op, t, t))
+    unops.append((f"GrB_ABS_{t}", "ABS", t, t))
+for t in INTS + UINTS:
+    unops.append((f"GrB_BNOT_{t}", "BNOT", t, t))
+unops.append(("GrB_LNOT", "LNOT", "BOOL", "BOOL"))
+FP_UNARY = ["SQRT", "LOG", "EXP", "LOG2", "SIN", "COS", "TAN", "ACOS", "ASIN", "ATAN", "SINH", "COSH", "TANH", "ACOSH",
+            "ASINH", "ATANH", "SIGNUM", "CEIL", "FLOOR", "ROUND", "TRUNC", "EXP2", "EXPM1", "LOG10", "LOG1P", "LGAMMA",
+            "TGAMMA", "ERF", "ERFC"]
+for t in FLOATS:
+    for op in FP_UNARY:
+        unops.append((f"GxB_{op}_{t}", op, t, t))
+    for op in ["ISINF", "ISNAN", "ISFINITE"]:
+        unops.append((f"GxB_{op}_{t}", op, t, "BOOL"))
+
 semirings = []   # (symbol, add op, add type, mul op, mul xtype)
 
 
@@ -124,6 +144,8 @@ def main():
         hdr.append(f"extern GrB_Monoid {sym};")
     for sym, *_ in semirings:
         hdr.append(f"extern GrB_Semiring {sym};")
+    for sym, *_ in unops:
+        hdr.append(f"extern GrB_UnaryOp {sym};")
     hdr.append("#endif")
     with open(os.path.join(ROOT, "include", "b200grb_ops.h"), "w") as f:
         f.write("\n".join(hdr) + "\n")
@@ -179,6 +201,13 @@ def main():
             inc.append(f"static GB_Semiring_opaque sr_{aop}_{mop}_{mt} = "
                        f"{{GB_MAGIC, &mon_{aop}_{at}, &bop_{mop}_{mt}, \"{sym}\", true}};")
         inc.append(f"GrB_Semiring {sym} = &{sdone[key]};")
+    udone = {}
+    for sym, op, xt, zt in unops:
+        key = (op, xt)
+        if key not in udone:
+            udone[key] = f"uop_{op}_{xt}"
+            inc.append(f"static GB_UnaryOp_opaque uop_{op}_{xt} = {{GB_MAGIC, UOP_{op}, &type_{xt}, &type_{zt}, \"{sym}\"}};")
+        inc.append(f"GrB_UnaryOp {sym} = &{udone[key]};")
     # name lookup table (B200_lookup)
     inc.append("struct GB_named { const char *name; int kind; void *obj; };")
     inc.append("static const GB_named gb_named_objects[] = {")
@@ -188,10 +217,12 @@ def main():
         inc.append(f"  {{\"{sym}\", 1, (void*)&{mdone[(op, t)]}}},")
     for sym, aop, at, mop, mt in semirings:
         inc.append(f"  {{\"{sym}\", 2, (void*)&{sdone[(aop, at, mop, mt)]}}},")
+    for sym, op, xt, zt in unops:
+        inc.append(f"  {{\"{sym}\", 3, (void*)&{udone[(op, xt)]}}},")
     inc.append("  {nullptr, 0, nullptr}};")
     with open(os.path.join(ROOT, "pygraphblas_b200", "csrc", "ops_table.inc"), "w") as f:
         f.write("\n".join(inc) + "\n")
-    print(f"binops={len(binops)} monoids={len(monoids)} semirings={len(semirings)}")
+    print(f"binops={len(binops)} monoids={len(monoids)} semirings={len(semirings)} unops={len(unops)}")
 
 
 if __name__ == "__main__":
