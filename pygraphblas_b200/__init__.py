@@ -20,6 +20,7 @@ from .ops import BinaryOp, Accum, Monoid, Semiring, current_semiring, current_ac
 from . import descriptor
 from .matrix import Matrix
 from .vector import Vector
+from .scalar import Scalar
 
 __all__ = ["lib", "ffi", "have_device", "Matrix", "Vector", "types", "descriptor", "Accum", "BinaryOp", "Monoid", "Semiring",
            "BOOL", "INT8", "INT16", "INT32", "INT64", "UINT8", "UINT16", "UINT32", "UINT64", "FP32", "FP64", "promote"]

@@ -158,6 +158,12 @@ DescFlags desc_flags(const GrB_Descriptor d);
 // (tpres NULL: every position present; t_scalar: tval is ONE value standing for all positions).  region
 // (NULL = everything) limits the write to the positions it flags, GrB_assign style.  own_t: T's buffers are
 // released here.
+struct Sc;
+// C<Mask> = accum(C, T) for a CSR T of type ttc (spgemm.cu); consumes T
+GrB_Info matrix_writeback(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const DescFlags &f,
+                          Csr &T, int ttc, bool t_already_masked, std::string *err);
+// fold of n values (presence bytes optional) with a builtin monoid operator on the device (vector_ops.cu)
+GrB_Info dev_reduce_values(const void *val, const uint8_t *pres, int vtc, int64_t n, int op, int mtc, Sc *out, bool *has, std::string *err);
 GrB_Info vector_write(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const DescFlags &f,
                       void *tval, uint8_t *tpres, int ttc, bool t_scalar, const uint8_t *region, bool own_t);
 
@@ -173,6 +179,9 @@ GrB_Info dev_count_present(const uint8_t *pres, int64_t n, int64_t *count, std::
 // (a float is held as the exactly-equal double).
 struct Sc { union { int64_t i; uint64_t u; double d; }; };
 struct GB_Scalar_opaque { int magic; GrB_Type type; bool has; Sc v; };     // GxB_Scalar (compat.cu)
+enum SelectCode : int { SEL_TRIL = 0, SEL_TRIU, SEL_DIAG, SEL_OFFDIAG, SEL_NONZERO, SEL_EQ_ZERO, SEL_GT_ZERO, SEL_GE_ZERO, SEL_LT_ZERO, SEL_LE_ZERO,
+                        SEL_NE_THUNK, SEL_EQ_THUNK, SEL_GT_THUNK, SEL_GE_THUNK, SEL_LT_THUNK, SEL_LE_THUNK };
+struct GB_SelectOp_opaque { int magic; const char *name; int code; };
 
 __host__ __device__ static inline int tc_size(int tc) {
     switch (tc) {

@@ -11,7 +11,6 @@
 #include <algorithm>
 #include "../../include/b200grb_compat.h"
 
-struct GB_SelectOp_opaque { int magic; const char *name; };
 
 static GB_Type_opaque type_FC32 = {GB_MAGIC, TC_COUNT, 8, "FC32"};
 static GB_Type_opaque type_FC64 = {GB_MAGIC, TC_COUNT + 1, 16, "FC64"};
@@ -20,7 +19,7 @@ extern "C" {
 GrB_Type GxB_FC32 = &type_FC32, GxB_FC64 = &type_FC64;
 const GrB_Index *GrB_ALL = &gb_all_sentinel;
 const double GxB_ALWAYS_HYPER = 1.0, GxB_NEVER_HYPER = -1.0, GxB_HYPER_DEFAULT = 0.0625;
-#define GB_SELOP(N) static GB_SelectOp_opaque selop_##N = {GB_MAGIC, "GxB_" #N}; GxB_SelectOp GxB_##N = &selop_##N;
+#define GB_SELOP(N) static GB_SelectOp_opaque selop_##N = {GB_MAGIC, "GxB_" #N, SEL_##N}; GxB_SelectOp GxB_##N = &selop_##N;
 GB_SELOP(TRIL) GB_SELOP(TRIU) GB_SELOP(DIAG) GB_SELOP(OFFDIAG) GB_SELOP(NONZERO) GB_SELOP(EQ_ZERO) GB_SELOP(GT_ZERO) GB_SELOP(GE_ZERO)
 GB_SELOP(LT_ZERO) GB_SELOP(LE_ZERO) GB_SELOP(NE_THUNK) GB_SELOP(EQ_THUNK) GB_SELOP(GT_THUNK) GB_SELOP(GE_THUNK) GB_SELOP(LT_THUNK) GB_SELOP(LE_THUNK)
 }
@@ -113,7 +112,7 @@ static GrB_Info reduce_values(void *c, int ctc, const GrB_BinaryOp accum, const 
     sc_store(ctc, c, 0, r);
     return GrB_SUCCESS;
 }
-static GrB_Info matrix_reduce(void *c, int ctc, const GrB_BinaryOp accum, const GrB_Monoid monoid, const GrB_Matrix A) {
+GrB_Info host_matrix_reduce(void *c, int ctc, const GrB_BinaryOp accum, const GrB_Monoid monoid, const GrB_Matrix A) {
     GB_LOCK;
     if (!gb_valid_matrix(A)) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "GrB_Matrix_reduce: invalid matrix");
     GB_TRY(matrix_ensure_host(A));
@@ -128,7 +127,7 @@ GrB_Info host_vector_reduce(void *c, int ctc, const GrB_BinaryOp accum, const Gr
 #define GB_COMPAT_TYPED(TN, CT, TC) \
     extern "C" GrB_Info GxB_Scalar_setElement_##TN(GxB_Scalar s, CT x) { return scalar_set(s, TC, &x); } \
     extern "C" GrB_Info GxB_Scalar_extractElement_##TN(CT *x, const GxB_Scalar s) { return scalar_get(x, TC, s); } \
-    extern "C" GrB_Info GrB_Matrix_reduce_##TN(CT *c, const GrB_BinaryOp accum, const GrB_Monoid m, const GrB_Matrix A, const GrB_Descriptor d) { (void)d; return matrix_reduce(c, TC, accum, m, A); }
+    /* GrB_Matrix_reduce_<T>: matrix_ops.cu */
 GB_COMPAT_TYPED(BOOL, bool, TC_BOOL) GB_COMPAT_TYPED(INT8, int8_t, TC_INT8) GB_COMPAT_TYPED(INT16, int16_t, TC_INT16) GB_COMPAT_TYPED(INT32, int32_t, TC_INT32)
 GB_COMPAT_TYPED(INT64, int64_t, TC_INT64) GB_COMPAT_TYPED(UINT8, uint8_t, TC_UINT8) GB_COMPAT_TYPED(UINT16, uint16_t, TC_UINT16)
 GB_COMPAT_TYPED(UINT32, uint32_t, TC_UINT32) GB_COMPAT_TYPED(UINT64, uint64_t, TC_UINT64) GB_COMPAT_TYPED(FP32, float, TC_FP32) GB_COMPAT_TYPED(FP64, double, TC_FP64)
@@ -143,8 +142,9 @@ static GrB_Info emult_check(const void *mask, const GrB_BinaryOp accum, const Gr
         return gb_fail(GrB_INVALID_VALUE, nullptr, "%s: mask / accumulator / transpose are not on the mxm/mxv/vxm hot path (not implemented by libb200grb)", fn);
     return GrB_SUCCESS;
 }
-extern "C" GrB_Info GrB_Matrix_eWiseMult_BinaryOp(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_BinaryOp op,
-                                                   const GrB_Matrix A, const GrB_Matrix B, const GrB_Descriptor desc) {
+// (with a CUDA device present the matrix form runs on the GPU: matrix_ops.cu)
+GrB_Info host_matrix_emult(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_BinaryOp op,
+                           const GrB_Matrix A, const GrB_Matrix B, const GrB_Descriptor desc) {
     GB_LOCK;
     if (!gb_valid_matrix(C) || !gb_valid_matrix(A) || !gb_valid_matrix(B)) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "GrB_Matrix_eWiseMult_BinaryOp: invalid matrix");
     GB_TRY(emult_check(Mask, accum, op, desc, "GrB_Matrix_eWiseMult_BinaryOp"));

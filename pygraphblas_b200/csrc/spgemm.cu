@@ -1078,8 +1078,8 @@ static GrB_Info matrix_finalize(const Csr *C, int ctc, const Csr &T, int ttc, co
 }
 
 // write T (type ttc) back into C under mask / accum / replace; consumes T
-static GrB_Info matrix_writeback(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const DescFlags &f,
-                                 Csr &T, int ttc, bool t_already_masked, std::string *err) {
+GrB_Info matrix_writeback(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const DescFlags &f,
+                          Csr &T, int ttc, bool t_already_masked, std::string *err) {
     const int ctc = C->type->code;
     const bool c_empty = C->host_valid ? (C->hi.empty() && C->pi.empty()) : (C->dev.nnz == 0);
     // fast exits: the result is exactly T

@@ -420,6 +420,25 @@ __global__ void __launch_bounds__(256) vec_reduce_kernel(const ReduceArgs a) {
         out[a.stage2 ? 0 : blockIdx.x] = r; oh[a.stage2 ? 0 : blockIdx.x] = (uint8_t)rh;
     }
 }
+GrB_Info dev_reduce_values(const void *val, const uint8_t *pres, int vtc, int64_t n, int op, int mtc, Sc *out, bool *has, std::string *err) {
+    out->u = 0; *has = false;
+    if (n <= 0) return GrB_SUCCESS;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256 * 8), (int64_t)G.num_sms * 8));
+    ReduceArgs a{};
+    a.n = n; a.val = val; a.pres = pres; a.vtc = vtc; a.op = op; a.mtc = mtc;
+    GB_TRY(dalloc(&a.part, (size_t)grid + 1, err));
+    GB_TRY(dalloc(&a.part_has, (size_t)grid + 1, err));
+    vec_reduce_kernel<<<grid, 256, 0, G.stream>>>(a); GB_LAUNCHED();
+    ReduceArgs b = a; b.n = grid; b.stage2 = 1;
+    vec_reduce_kernel<<<1, 256, 0, G.stream>>>(b); GB_LAUNCHED();
+    uint8_t rh = 0;
+    CU_TRY(cudaMemcpyAsync(out, a.part + grid, sizeof(Sc), cudaMemcpyDeviceToHost, G.stream), err);
+    CU_TRY(cudaMemcpyAsync(&rh, a.part_has + grid, 1, cudaMemcpyDeviceToHost, G.stream), err);
+    CU_TRY(cudaStreamSynchronize(G.stream), err);
+    dfree(a.part); dfree(a.part_has);
+    *has = rh != 0;
+    return GrB_SUCCESS;
+}
 static GrB_Info vec_reduce(void *c, int ctc, const GrB_BinaryOp accum, const GrB_Monoid monoid, const GrB_Vector u, const char *fn) {
     if (!G.have_device) return host_vector_reduce(c, ctc, accum, monoid, u);        // Vector.iseq of the handle-plumbing tests
     if (!c || !monoid) return gb_fail(GrB_NULL_POINTER, nullptr, "%s: NULL argument", fn);
@@ -429,20 +448,8 @@ static GrB_Info vec_reduce(void *c, int ctc, const GrB_BinaryOp accum, const GrB
     if (op->opcode == OP_USER || (accum && accum->opcode == OP_USER)) return gb_fail(GrB_INVALID_VALUE, nullptr, "%s: user-defined operators cannot run on the GPU", fn);
     GB_TRY(vector_ensure_device(u));
     const int mtc = op->ztype->code;
-    const int64_t n = (int64_t)u->n;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256 * 8), (int64_t)G.num_sms * 8));
-    ReduceArgs a{};
-    a.n = n; a.val = u->dval; a.pres = u->dpres; a.vtc = u->type->code; a.op = op->opcode; a.mtc = mtc;
-    GB_TRY(dalloc(&a.part, (size_t)grid + 1, &u->err));
-    GB_TRY(dalloc(&a.part_has, (size_t)grid + 1, &u->err));
-    vec_reduce_kernel<<<grid, 256, 0, G.stream>>>(a); GB_LAUNCHED();
-    ReduceArgs b = a; b.n = grid; b.stage2 = 1;
-    vec_reduce_kernel<<<1, 256, 0, G.stream>>>(b); GB_LAUNCHED();
-    Sc r; r.u = 0; uint8_t rh = 0;
-    CU_TRY(cudaMemcpyAsync(&r, a.part + grid, sizeof(Sc), cudaMemcpyDeviceToHost, G.stream), &u->err);
-    CU_TRY(cudaMemcpyAsync(&rh, a.part_has + grid, 1, cudaMemcpyDeviceToHost, G.stream), &u->err);
-    CU_TRY(cudaStreamSynchronize(G.stream), &u->err);
-    dfree(a.part); dfree(a.part_has);
+    Sc r; bool rh = false;
+    GB_TRY(dev_reduce_values(u->dval, u->dpres, u->type->code, (int64_t)u->n, op->opcode, mtc, &r, &rh, &u->err));
     const Sc acc = rh ? r : sc_monoid_identity(op->opcode, mtc);
     Sc out = sc_cast(acc, mtc, ctc);
     if (accum) {

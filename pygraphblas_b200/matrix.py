@@ -287,6 +287,166 @@ class Matrix:
         _check(lib.GrB_mxv(out._vector[0], mask, accum, semiring.get_op(), self._matrix[0], other._vector[0], desc))
         return out
 
+    # ------------------------------------------------------------------ consumers of the hot path (matrix_ops.cu)
+    _SELECT = {">": "GT_THUNK", "<": "LT_THUNK", ">=": "GE_THUNK", "<=": "LE_THUNK", "!=": "NE_THUNK", "==": "EQ_THUNK",
+               ">0": "GT_ZERO", "<0": "LT_ZERO", ">=0": "GE_ZERO", "<=0": "LE_ZERO", "!=0": "NONZERO", "==0": "EQ_ZERO"}
+
+    def select(self, op, thunk=None, out=None, mask=None, accum=None, desc=None):
+        """C<mask> = accum(C, select(A, thunk))  (matrix.py:2042-2140 of the reference)."""
+        from .scalar import Scalar
+        if out is None:
+            out = Matrix.sparse(self.type, self.nrows, self.ncols)
+        if isinstance(op, str):
+            op = getattr(lib, "GxB_" + self._SELECT[op])
+        keep = None
+        if thunk is None:
+            thunk = NULL
+        elif isinstance(thunk, (bool, int, float)):
+            keep = Scalar.from_value(thunk); thunk = keep._scalar[0]
+        elif isinstance(thunk, Scalar):
+            keep = thunk; thunk = keep._scalar[0]
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(lib.GxB_Matrix_select(out._matrix[0], mask, accum, op, self._matrix[0], thunk, desc))
+        return out
+
+    def tril(self, offset=None):
+        """(matrix.py:2142-2170)"""
+        return self.select(lib.GxB_TRIL, offset)
+
+    def triu(self, offset=None):
+        """(matrix.py:2172-2200)"""
+        return self.select(lib.GxB_TRIU, offset)
+
+    def diag(self, offset=None):
+        return self.select(lib.GxB_DIAG, offset)
+
+    def offdiag(self, offset=None):
+        """(matrix.py:2279-2307)"""
+        return self.select(lib.GxB_OFFDIAG, offset)
+
+    def nonzero(self):
+        """(matrix.py:2309-2311)"""
+        return self.select(lib.GxB_NONZERO)
+
+    def apply(self, op, out=None, mask=None, accum=None, desc=None):
+        """(matrix.py:1934-1963)"""
+        if out is None:
+            out = Matrix.sparse(self.type, self.nrows, self.ncols)
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(lib.GrB_Matrix_apply(out._matrix[0], mask, accum, op.get_op(), self._matrix[0], desc))
+        return out
+
+    def apply_first(self, first, op, out=None, mask=None, accum=None, desc=None):
+        """(matrix.py:1965-2005)"""
+        if out is None:
+            out = Matrix.sparse(self.type, self.nrows, self.ncols)
+        typ = types.from_python(first)
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(typ._Matrix_apply_BinaryOp1st(out._matrix[0], mask, accum, op.get_op(), typ.from_value(first), self._matrix[0], desc))
+        return out
+
+    def apply_second(self, op, second, out=None, mask=None, accum=None, desc=None):
+        """(matrix.py:2007-2040)"""
+        if out is None:
+            out = Matrix.sparse(self.type, self.nrows, self.ncols)
+        typ = types.from_python(second)
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(typ._Matrix_apply_BinaryOp2nd(out._matrix[0], mask, accum, op.get_op(), self._matrix[0], typ.from_value(second), desc))
+        return out
+
+    def pattern(self, typ=types.BOOL, out=None):
+        """(matrix.py:887-902)"""
+        if out is None:
+            out = Matrix.sparse(typ, self.nrows, self.ncols)
+        return self.apply(typ.ONE, out=out)
+
+    def eadd(self, other, add_op=None, cast=None, out=None, mask=None, accum=None, desc=None):
+        """Element-wise union (matrix.py:1103-1264; also `|`, `+`, `-`)."""
+        from .ops import Monoid, Semiring
+        func = lib.GrB_Matrix_eWiseAdd_BinaryOp
+        if isinstance(add_op, Monoid):
+            func = lib.GrB_Matrix_eWiseAdd_Monoid
+        elif isinstance(add_op, Semiring):
+            func = lib.GrB_Matrix_eWiseAdd_Semiring
+        if out is None:
+            out = Matrix.sparse(cast or types.promote(self.type, other.type), self.nrows, self.ncols)
+        if add_op is None:
+            add_op = out.type._default_addop()
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(func(out._matrix[0], mask, accum, add_op.get_op(), self._matrix[0], other._matrix[0], desc))
+        return out
+
+    def emult(self, other, mult_op=None, cast=None, out=None, mask=None, accum=None, desc=None):
+        """Element-wise intersection (matrix.py:1266-1415; also `&`, `*`, `/`)."""
+        if out is None:
+            out = Matrix.sparse(cast or types.promote(self.type, other.type), self.nrows, self.ncols)
+        if mult_op is None:
+            mult_op = out.type._default_multop()
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(lib.GrB_Matrix_eWiseMult_BinaryOp(out._matrix[0], mask, accum, mult_op.get_op(), self._matrix[0], other._matrix[0], desc))
+        return out
+
+    def _reduce(self, typ, mon, accum=None):
+        if mon is None:
+            mon = getattr(typ, "LOR_MONOID" if typ is types.BOOL else "PLUS_MONOID")
+        x = ffi.new(typ.ptr)
+        _, accum, desc = self._get_args(None, accum, None)
+        _check(typ._Matrix_reduce(x, accum, mon.get_op(), self._matrix[0], desc))
+        return typ.from_value(x[0])
+
+    def reduce_bool(self, mon=None, **kw):
+        """(matrix.py:1759-1780)"""
+        return self._reduce(types.BOOL, mon, **kw)
+
+    def reduce_int(self, mon=None, **kw):
+        """(matrix.py:1782-1804)"""
+        return self._reduce(types.INT64, mon, **kw)
+
+    def reduce_float(self, mon=None, **kw):
+        """(matrix.py:1806-1828)"""
+        return self._reduce(types.FP64, mon, **kw)
+
+    def reduce_vector(self, mon=None, out=None, mask=None, accum=None, desc=None):
+        """w<mask> = accum(w, reduce rows of op(A))  (matrix.py:1861-1932)."""
+        from .vector import Vector
+        if mon is None:
+            mon = getattr(self.type, "LOR_MONOID" if self.type is types.BOOL else "PLUS_MONOID")
+        if out is None:
+            d = desc if desc is not None else current_desc.get(None)
+            out = Vector.sparse(self.type, self.ncols if (d is not None and _T0 in d) else self.nrows)
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(lib.GrB_Matrix_reduce_Monoid(out._vector[0], mask, accum, mon.get_op(), self._matrix[0], desc))
+        return out
+
+    def _scalar_or_matrix(self, other, mat_fn, op, first=False):
+        if isinstance(other, Matrix):
+            return mat_fn(other, op)
+        return self.apply_first(other, op) if first else self.apply_second(op, other)
+
+    def __add__(self, o):
+        return self._scalar_or_matrix(o, self.eadd, self.type.PLUS)
+
+    def __sub__(self, o):
+        return self._scalar_or_matrix(o, self.eadd, self.type.MINUS)
+
+    def __mul__(self, o):
+        return self._scalar_or_matrix(o, self.emult, self.type.TIMES)
+
+    def __truediv__(self, o):
+        return self._scalar_or_matrix(o, self.emult, self.type.DIV)
+
+    def __or__(self, o):
+        return self.eadd(o)
+
+    def __and__(self, o):
+        return self.emult(o)
+
+    def __neg__(self):
+        return self.apply(self.type.AINV)
+
+    def __abs__(self):
+        return self.apply(self.type.ABS)
+
     def __matmul__(self, other):
         from .vector import Vector
         if isinstance(other, Matrix):

@@ -33,6 +33,9 @@ class Type:
         self._Vector_apply_BinaryOp1st = fn("Vector_apply_BinaryOp1st")
         self._Vector_apply_BinaryOp2nd = fn("Vector_apply_BinaryOp2nd")
         self._Vector_reduce = fn("Vector_reduce")
+        self._Matrix_reduce = fn("Matrix_reduce")
+        self._Matrix_apply_BinaryOp1st = fn("Matrix_apply_BinaryOp1st")
+        self._Matrix_apply_BinaryOp2nd = fn("Matrix_apply_BinaryOp2nd")
 
     def _default_addop(self):                                           # types.py:157-160
         return self.LOR if self is BOOL else self.PLUS
