@@ -19,7 +19,7 @@ GxB_INDEX_MAX = 1 << 60
 
 
 class Matrix:
-    __slots__ = ("_matrix", "_keep", "__weakref__")
+    __slots__ = ("_matrix", "_keep", "_mask_alive", "__weakref__")
 
     def __init__(self, handle):
         """Wrap a raw GrB_Matrix* (ffi.new("GrB_Matrix*")); the type is read back from the
@@ -227,6 +227,7 @@ class Matrix:
         defaults (matrix.py:2380-2399)."""
         from .vector import Vector
         if isinstance(mask, Matrix):
+            self._mask_alive = mask            # a temporary passed as mask= must outlive the call
             mask = mask._matrix[0]
         elif isinstance(mask, Vector):
             mask = mask._vector[0]

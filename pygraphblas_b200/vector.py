@@ -14,7 +14,7 @@ GxB_INDEX_MAX = 1 << 60
 
 
 class Vector:
-    __slots__ = ("_vector", "__weakref__")
+    __slots__ = ("_vector", "_mask_alive", "__weakref__")
 
     def __init__(self, handle):
         self._vector = handle
@@ -199,6 +199,7 @@ class Vector:
     def _get_args(self, mask=None, accum=None, desc=None):
         """(vector.py:1078-1099)"""
         if isinstance(mask, Vector):
+            self._mask_alive = mask            # a temporary passed as mask= must outlive the call
             mask = mask._vector[0]
         else:
             mask = NULL

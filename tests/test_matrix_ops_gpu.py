@@ -118,7 +118,7 @@ def test_random_select_apply_reduce(seed):
     _csr_equal(A.nonzero(), _keep(S, lambda i, j, x: x != 0))
     _csr_equal(A.select(">", 1), _keep(S, lambda i, j, x: x > 1))
     _csr_equal(A.select("<=0"), _keep(S, lambda i, j, x: x <= 0))
-    _csr_equal(A.select(lib.GxB_TRIL, 0, desc=descriptor.T0), _keep(S.T.tocsr(), lambda i, j, x: j <= i))
+    _csr_equal(A.select(lib.GxB_TRIL, 0, out=Matrix.sparse(typ, n, m), desc=descriptor.T0), _keep(S.T.tocsr(), lambda i, j, x: j <= i))
     Z = S.copy(); Z.data = np.abs(Z.data)
     _csr_equal(A.apply(typ.ABS), Z)
     Z = S.copy(); Z.data = (Z.data * dt(3)).astype(dt)
