@@ -549,6 +549,21 @@ __host__ __device__ static inline Sc sc_monoid_identity(int op, int tc) {
     return acc;
 }
 
+// value of a mask entry as a truth value (any builtin type), without the carrier
+__host__ __device__ static inline bool mask_value_true(int mtc, const void *mval, int64_t i) {
+    switch (mtc) {
+        case TC_FP32: return ((const float *)mval)[i] != 0.0f;
+        case TC_FP64: return ((const double *)mval)[i] != 0.0;
+        default: break;
+    }
+    switch (tc_size(mtc)) {
+        case 1: return ((const uint8_t *)mval)[i] != 0;
+        case 2: return ((const uint16_t *)mval)[i] != 0;
+        case 4: return ((const uint32_t *)mval)[i] != 0;
+        default: return ((const uint64_t *)mval)[i] != 0;
+    }
+}
+
 // ---------------------------------------------------------------- launch helpers
 __host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 #define GB_LAUNCHED() (G.launches++)

@@ -502,6 +502,16 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
         // the run-time-operator kernel reads both operands: make sure both are of the operand type
         if (aval == c.val && A->type->code != xt) { GB_TRY(dev_cast_values(&a_cast, xt, c.val, A->type->code, c.nnz, err)); aval = a_cast; }
         if (uval == u->dval && u->type->code != xt) { GB_TRY(dev_cast_values(&u_cast, xt, u->dval, u->type->code, (int64_t)u->n, err)); uval = u_cast; }
+        // few frontier edges: push along the rows of the other orientation (already in HBM) instead of pulling every row
+        bool pushed = false;
+        const Csr &o = use_transpose ? A->dev : A->devT;
+        if (sparse_u && o.valid && o.rowptr32 && o.nnz == c.nnz && A->type->code == xt && getenv("B200GRB_NO_PUSH") == nullptr) {
+            PushArgs ps{};
+            ps.rowptr = o.rowptr32; ps.col = o.col; ps.aval = o.val; ps.nin = o.nrows; ps.uval = uval; ps.upres = u->dpres;
+            ps.mval = mask->dval; ps.mpres = mask->dpres; ps.mtc = mask->type->code; ps.mask_comp = f.mask_comp; ps.mask_struct = f.mask_struct;
+            ps.tval = tval; ps.tpres = tpres; ps.nout = n; ps.add_op = add; ps.mul_op = kmul; ps.flip = kflip;
+            GB_TRY(spmv_masked_push_try(xt, zt, ps, c.nnz, &pushed, err));
+        }
         PullArgs pa{};
         pa.rowptr = c.rowptr32; pa.col = c.col; pa.aval = aval; pa.nrows = c.nrows; pa.uval = uval; pa.upres = u->dpres;
         pa.mval = mask->dval; pa.mpres = mask->dpres; pa.mtc = mask->type->code; pa.mask_comp = f.mask_comp; pa.mask_struct = f.mask_struct;
@@ -511,7 +521,7 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
         GB_TRY(dalloc(&pa.long_rows, (size_t)pa.long_cap + 1, err));
         GB_TRY(dalloc(&pa.long_count, 4, err));
         CU_TRY(cudaMemsetAsync(pa.long_count, 0, sizeof(int), G.stream), err);
-        GrB_Info r = spmv_masked_pull_dispatch(xt, zt, pa, err);
+        GrB_Info r = pushed ? GrB_SUCCESS : spmv_masked_pull_dispatch(xt, zt, pa, err);
         dfree(pa.long_rows); dfree(pa.long_count);
         if (r != GrB_SUCCESS) { dfree(tval); dfree(tpres); dfree(a_cast); dfree(u_cast); return r; }
     }

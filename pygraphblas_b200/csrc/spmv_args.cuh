@@ -31,3 +31,18 @@ struct PullArgs {
     uint32_t *long_rows; int *long_count;                      // work list of the rows left to the CTA-per-row kernel
 };
 constexpr uint32_t PULL_LONG = 4096;          // rows longer than this go to the CTA-per-row kernel
+
+// ------------------------------------------------------------------ masked push for small frontiers (same three monoids)
+// The transpose of the pull: for every present u(k), walk row k of the OTHER orientation's CSR and store into
+// T(j) for the columns j the mask lets through.  LOR / LAND / ANY need no atomics: T(j) starts at the monoid's
+// identity-like value and every store is idempotent (LOR: "a product was true", LAND: "a product was false",
+// ANY: any product).  Work is proportional to the frontier's out-edges; used when those are < nnz / 16.
+struct PushArgs {
+    const uint32_t *rowptr; const uint32_t *col; const void *aval; int64_t nin;    // CSR whose rows are the input positions k
+    const void *uval; const uint8_t *upres;
+    const void *mval; const uint8_t *mpres; int mtc; int mask_comp, mask_struct;
+    void *tval; uint8_t *tpres; int64_t nout;
+    int add_op, mul_op, flip;
+    uint32_t *list; int64_t *chunk_scan; unsigned long long *counters;           // frontier list, chunk offsets, {count, edges}
+};
+GrB_Info spmv_masked_push_try(int xt, int zt, PushArgs &a, int64_t nnz_total, bool *done, std::string *err);

@@ -166,3 +166,122 @@ GrB_Info spmv_masked_pull_dispatch(int xt, int zt, const PullArgs &a, std::strin
     return gb_fail(GrB_DOMAIN_MISMATCH, err, "mxv: unsupported semiring domains (x=%d, z=%d)", xt, zt);
 }
 
+
+// ------------------------------------------------------------------ push
+constexpr int PUSH_CHUNK = 1024;
+__global__ void __launch_bounds__(256) push_frontier_kernel(const PushArgs a) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < a.nin; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = base + lane;
+        const bool in = k < a.nin && (!a.upres || a.upres[k] != 0);
+        const unsigned long long deg = in ? (unsigned long long)(a.rowptr[k + 1] - a.rowptr[k]) : 0ull;
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (!m) continue;
+        unsigned long long pos = 0;
+        if (lane == 0) pos = atomicAdd(&a.counters[0], (unsigned long long)__popc(m));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (in) a.list[pos + __popc(m & ((1u << lane) - 1u))] = (uint32_t)k;
+        unsigned long long d = deg;
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (lane == 0 && d) atomicAdd(&a.counters[1], d);
+    }
+}
+__global__ void push_chunks_kernel(const PushArgs a, int64_t count) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= count; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t c = 0;
+        if (i < count) { const uint32_t k = a.list[i]; c = ((int64_t)(a.rowptr[k + 1] - a.rowptr[k]) + PUSH_CHUNK - 1) / PUSH_CHUNK; }
+        a.chunk_scan[i] = c;
+    }
+}
+template <typename ZT> __global__ void push_init_kernel(ZT *tval, uint8_t *tpres, int64_t n, ZT init) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { tval[i] = init; tpres[i] = 0; }
+}
+// one warp per chunk of <= PUSH_CHUNK entries of a frontier row
+template <typename XT, typename ZT>
+__global__ void __launch_bounds__(256) push_kernel(const PushArgs a, int64_t count) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nchunks = a.chunk_scan[count];
+    const XT *aval = static_cast<const XT *>(a.aval), *uval = static_cast<const XT *>(a.uval);
+    ZT *tval = static_cast<ZT *>(a.tval);
+    for (int64_t c = warp; c < nchunks; c += nwarps) {
+        int64_t lo = 0, hi = count;                              // owner: last i with chunk_scan[i] <= c
+        while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (a.chunk_scan[mid] <= c) lo = mid; else hi = mid; }
+        const uint32_t k = a.list[lo];
+        const uint32_t rs = a.rowptr[k] + (uint32_t)(c - a.chunk_scan[lo]) * PUSH_CHUNK;
+        const uint32_t re = min(a.rowptr[k + 1], rs + (uint32_t)PUSH_CHUNK);
+        const XT uk = gload<XT>(uval + k);
+        for (uint32_t e = rs + lane; e < re; e += 32) {
+            const uint32_t j = __ldg(a.col + e);
+            bool m = a.mpres ? a.mpres[j] != 0 : true;
+            if (m && !a.mask_struct) m = mask_value_true(a.mtc, a.mval, (int64_t)j);
+            if (a.mask_comp) m = !m;
+            if (!m) continue;
+            const XT av = gload<XT>(aval + e);
+            const ZT v = a.flip ? MulApply<XT, ZT>::f(a.mul_op, uk, av) : MulApply<XT, ZT>::f(a.mul_op, av, uk);
+            a.tpres[j] = 1;
+            if (a.add_op == OP_LOR) { if (v != (ZT)0) tval[j] = (ZT)1; }
+            else if (a.add_op == OP_LAND) { if (v == (ZT)0) tval[j] = (ZT)0; }
+            else tval[j] = v;
+        }
+    }
+}
+template <typename XT, typename ZT> static void push_launch(const PushArgs &a, int64_t count, int64_t chunk_bound) {
+    const ZT init = a.add_op == OP_LAND ? (ZT)1 : (ZT)0;
+    const int g0 = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a.nout, 256), (int64_t)G.num_sms * 16));
+    push_init_kernel<ZT><<<g0, 256, 0, G.stream>>>(static_cast<ZT *>(a.tval), a.tpres, a.nout, init); GB_LAUNCHED();
+    if (count > 0) {
+        const int g1 = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(chunk_bound * 32, 256), (int64_t)G.num_sms * 16));
+        push_kernel<XT, ZT><<<g1, 256, 0, G.stream>>>(a, count); GB_LAUNCHED();
+    }
+}
+GrB_Info spmv_masked_push_try(int xt, int zt, PushArgs &a, int64_t nnz_total, bool *done, std::string *err) {
+    *done = false;
+    // LOR / LAND results are normalised only when the monoid type is BOOL (every builtin); ANY stores the product as is
+    if ((a.add_op == OP_LOR || a.add_op == OP_LAND) && zt != TC_BOOL) return GrB_SUCCESS;
+    if (!(xt == zt || zt == TC_BOOL)) return GrB_SUCCESS;
+    GB_TRY(dalloc(&a.list, (size_t)a.nin + 1, err));
+    GB_TRY(dalloc(&a.counters, 2, err));
+    CU_TRY(cudaMemsetAsync(a.counters, 0, 16, G.stream), err);
+    const int g = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a.nin, 256), (int64_t)G.num_sms * 16));
+    push_frontier_kernel<<<g, 256, 0, G.stream>>>(a); GB_LAUNCHED();
+    unsigned long long h[2] = {0, 0};
+    CU_TRY(cudaMemcpyAsync(h, a.counters, 16, cudaMemcpyDeviceToHost, G.stream), err);
+    CU_TRY(cudaStreamSynchronize(G.stream), err);
+    const int64_t count = (int64_t)h[0], edges = (int64_t)h[1];
+    if (edges * 16 > nnz_total && getenv("B200GRB_FORCE_PUSH") == nullptr) { dfree(a.list); dfree(a.counters); a.list = nullptr; return GrB_SUCCESS; }
+    GB_TRY(dalloc(&a.chunk_scan, (size_t)count + 2, err));
+    if (count > 0) {
+        const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(count + 1, 256), (int64_t)G.num_sms * 16));
+        push_chunks_kernel<<<g2, 256, 0, G.stream>>>(a, count); GB_LAUNCHED();
+        GB_TRY(dev_exclusive_scan(a.chunk_scan, count + 1, err));
+    } else CU_TRY(cudaMemsetAsync(a.chunk_scan, 0, 16, G.stream), err);
+    const int64_t chunk_bound = edges / PUSH_CHUNK + count + 1;
+    bool ok = true;
+#define GB_PUSH(XT_, ZT_) do { push_launch<XT_, ZT_>(a, count, chunk_bound); } while (0)
+    if (xt == zt) {
+        switch (xt) {
+#define GB_GEN(TC, T) case TC: GB_PUSH(T, T); break;
+            GB_GEN(TC_BOOL, bool) GB_GEN(TC_INT8, int8_t) GB_GEN(TC_INT16, int16_t) GB_GEN(TC_INT32, int32_t) GB_GEN(TC_INT64, int64_t)
+            GB_GEN(TC_UINT8, uint8_t) GB_GEN(TC_UINT16, uint16_t) GB_GEN(TC_UINT32, uint32_t) GB_GEN(TC_UINT64, uint64_t)
+            GB_GEN(TC_FP32, float) GB_GEN(TC_FP64, double)
+#undef GB_GEN
+            default: ok = false;
+        }
+    } else {
+        switch (xt) {
+#define GB_GEN(TC, T) case TC: GB_PUSH(T, bool); break;
+            GB_GEN(TC_INT8, int8_t) GB_GEN(TC_INT16, int16_t) GB_GEN(TC_INT32, int32_t) GB_GEN(TC_INT64, int64_t)
+            GB_GEN(TC_UINT8, uint8_t) GB_GEN(TC_UINT16, uint16_t) GB_GEN(TC_UINT32, uint32_t) GB_GEN(TC_UINT64, uint64_t)
+            GB_GEN(TC_FP32, float) GB_GEN(TC_FP64, double)
+#undef GB_GEN
+            default: ok = false;
+        }
+    }
+#undef GB_PUSH
+    dfree(a.list); dfree(a.counters); dfree(a.chunk_scan);
+    a.list = nullptr;
+    CU_TRY(cudaGetLastError(), err);
+    *done = ok;
+    return GrB_SUCCESS;
+}

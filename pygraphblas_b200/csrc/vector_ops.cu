@@ -64,6 +64,66 @@ __global__ void vec_finalize_kernel(const VecFinalizeArgs a) {
     }
 }
 
+// The same write-back when w, T and the accumulator share one type T (the iterated cases: SSSP's
+// v = min(v, t), BFS's q<!visited> = t, PageRank's r += t): no carrier, no casts, the operator applied on T.
+template <typename T> struct VecFinalizeTyped {
+    int64_t n;
+    const T *wval; const uint8_t *wpres; int w_exists;
+    const T *tval; const uint8_t *tpres;
+    const void *mval; const uint8_t *mpres; int mtc; int has_mask, mask_comp, mask_struct, replace;
+    int accum_op;                        // < 0: none
+    T *oval; uint8_t *opres;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) vec_finalize_typed_kernel(const VecFinalizeTyped<T> a) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool tp = a.tpres ? a.tpres[i] != 0 : true;
+        const bool wp = a.w_exists ? (a.wpres ? a.wpres[i] != 0 : true) : false;
+        bool m = true;
+        if (a.has_mask) {
+            m = a.mpres ? a.mpres[i] != 0 : true;
+            if (m && !a.mask_struct) m = mask_value_true(a.mtc, a.mval, i);
+            if (a.mask_comp) m = !m;
+        }
+        T out = (T)0; bool op = false;
+        if (m) {
+            if (a.accum_op >= 0) {
+                if (wp && tp) { out = op_apply<T>(a.accum_op, a.wval[i], a.tval[i]); op = true; }
+                else if (wp) { out = a.wval[i]; op = true; }
+                else if (tp) { out = a.tval[i]; op = true; }
+            } else if (tp) { out = a.tval[i]; op = true; }
+        } else if (!a.replace && wp) { out = a.wval[i]; op = true; }
+        if (op) a.oval[i] = out;
+        if (a.opres) a.opres[i] = op;
+    }
+}
+template <typename T> static void launch_finalize_typed(const VecFinalizeArgs &g) {
+    VecFinalizeTyped<T> a{};
+    a.n = g.n; a.wval = (const T *)g.wval; a.wpres = g.wpres; a.w_exists = g.w_exists; a.tval = (const T *)g.tval; a.tpres = g.tpres;
+    a.mval = g.mval; a.mpres = g.mpres; a.mtc = g.mtc; a.has_mask = g.has_mask; a.mask_comp = g.mask_comp; a.mask_struct = g.mask_struct;
+    a.replace = g.replace; a.accum_op = g.accum_op; a.oval = (T *)g.oval; a.opres = g.opres;
+    vec_finalize_typed_kernel<T><<<vgrid(g.n), 256, 0, G.stream>>>(a); GB_LAUNCHED();
+}
+static bool finalize_typed(const VecFinalizeArgs &g) {
+    // one type throughout, whole-vector write, per-position T, accumulator (if any) of that type with a same-type result
+    if (g.wtc != g.ttc || g.t_scalar || g.region) return false;
+    if (g.accum_op >= 0 && (g.accum_tc != g.wtc || g.accum_ztc != g.wtc || g.accum_op >= OP_EQ)) return false;
+    switch (g.wtc) {
+        case TC_BOOL: launch_finalize_typed<bool>(g); return true;
+        case TC_INT8: launch_finalize_typed<int8_t>(g); return true;
+        case TC_INT16: launch_finalize_typed<int16_t>(g); return true;
+        case TC_INT32: launch_finalize_typed<int32_t>(g); return true;
+        case TC_INT64: launch_finalize_typed<int64_t>(g); return true;
+        case TC_UINT8: launch_finalize_typed<uint8_t>(g); return true;
+        case TC_UINT16: launch_finalize_typed<uint16_t>(g); return true;
+        case TC_UINT32: launch_finalize_typed<uint32_t>(g); return true;
+        case TC_UINT64: launch_finalize_typed<uint64_t>(g); return true;
+        case TC_FP32: launch_finalize_typed<float>(g); return true;
+        case TC_FP64: launch_finalize_typed<double>(g); return true;
+        default: return false;
+    }
+}
+
 GrB_Info vector_write(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const DescFlags &f,
                       void *tval, uint8_t *tpres, int ttc, bool t_scalar, const uint8_t *region, bool own_t) {
     std::string *err = &w->err;
@@ -100,7 +160,7 @@ GrB_Info vector_write(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp ac
     const bool out_full = (w_full && !(mask && f.replace) && (accum != nullptr || (region != nullptr && tpres == nullptr))) ||
                           (tpres == nullptr && !mask && !region);
     if (!out_full) GB_TRY(dmalloc((void **)&fa.opres, (size_t)n + 16, err));
-    vec_finalize_kernel<<<vgrid(n), 256, 0, G.stream>>>(fa); GB_LAUNCHED();
+    if (!finalize_typed(fa)) { vec_finalize_kernel<<<vgrid(n), 256, 0, G.stream>>>(fa); GB_LAUNCHED(); }
     if (own_t) { dfree(tval); dfree(tpres); }
     vector_adopt_device(w, fa.oval, fa.opres);
     CU_TRY(cudaGetLastError(), err);

@@ -242,6 +242,14 @@ def test_masked_pull_hub_rows_against_oracle(k):
     _check(case, util.product_run(case))
 
 
+@pytest.mark.parametrize("k", range(1, len(PULL_CASES) * 3, 2))
+def test_masked_push_forced_against_oracle(k, monkeypatch):
+    """The same cases in their vxm form with the push kernel forced for every frontier size (the other
+    orientation of A is in HBM for vxm, so push is available): idempotent stores must reproduce the fold."""
+    monkeypatch.setenv("B200GRB_FORCE_PUSH", "1")
+    test_masked_pull_hub_rows_against_oracle(k)
+
+
 def test_rmat_triangle_count_masked_mxm():
     """configs[3] shape: C<L> = L (+.pair) L on the strict lower triangle of A + A' (masked hash SpGEMM),
     and the masked-dot form C<L> = L L' (descriptor ST1); both against the CPU port and scipy."""
