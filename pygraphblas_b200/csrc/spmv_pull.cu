@@ -169,21 +169,32 @@ GrB_Info spmv_masked_pull_dispatch(int xt, int zt, const PullArgs &a, std::strin
 
 // ------------------------------------------------------------------ push
 constexpr int PUSH_CHUNK = 1024;
+// size of the frontier and of its out-edge set: one atomic pair per CTA
+__global__ void __launch_bounds__(256) push_stats_kernel(const PushArgs a) {
+    __shared__ unsigned long long s_c[8], s_d[8];
+    unsigned long long cnt = 0, deg = 0;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < a.nin; k += (int64_t)gridDim.x * blockDim.x)
+        if (!a.upres || a.upres[k] != 0) { ++cnt; deg += (unsigned long long)(a.rowptr[k + 1] - a.rowptr[k]); }
+    for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); deg += __shfl_xor_sync(0xffffffffu, deg, o); }
+    if ((threadIdx.x & 31) == 0) { s_c[threadIdx.x >> 5] = cnt; s_d[threadIdx.x >> 5] = deg; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < 8; ++q) { cnt += s_c[q]; deg += s_d[q]; }
+        if (cnt) { atomicAdd(&a.counters[0], cnt); atomicAdd(&a.counters[1], deg); }
+    }
+}
+// the frontier as a list (order irrelevant): warp-aggregated append
 __global__ void __launch_bounds__(256) push_frontier_kernel(const PushArgs a) {
     const int lane = threadIdx.x & 31;
     for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < a.nin; base += (int64_t)gridDim.x * blockDim.x) {
         const int64_t k = base + lane;
         const bool in = k < a.nin && (!a.upres || a.upres[k] != 0);
-        const unsigned long long deg = in ? (unsigned long long)(a.rowptr[k + 1] - a.rowptr[k]) : 0ull;
         const unsigned m = __ballot_sync(0xffffffffu, in);
         if (!m) continue;
         unsigned long long pos = 0;
-        if (lane == 0) pos = atomicAdd(&a.counters[0], (unsigned long long)__popc(m));
+        if (lane == 0) pos = atomicAdd(&a.counters[2], (unsigned long long)__popc(m));
         pos = __shfl_sync(0xffffffffu, pos, 0);
         if (in) a.list[pos + __popc(m & ((1u << lane) - 1u))] = (uint32_t)k;
-        unsigned long long d = deg;
-        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        if (lane == 0 && d) atomicAdd(&a.counters[1], d);
     }
 }
 __global__ void push_chunks_kernel(const PushArgs a, int64_t count) {
@@ -240,16 +251,20 @@ GrB_Info spmv_masked_push_try(int xt, int zt, PushArgs &a, int64_t nnz_total, bo
     // LOR / LAND results are normalised only when the monoid type is BOOL (every builtin); ANY stores the product as is
     if ((a.add_op == OP_LOR || a.add_op == OP_LAND) && zt != TC_BOOL) return GrB_SUCCESS;
     if (!(xt == zt || zt == TC_BOOL)) return GrB_SUCCESS;
-    GB_TRY(dalloc(&a.list, (size_t)a.nin + 1, err));
-    GB_TRY(dalloc(&a.counters, 2, err));
-    CU_TRY(cudaMemsetAsync(a.counters, 0, 16, G.stream), err);
-    const int g = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a.nin, 256), (int64_t)G.num_sms * 16));
-    push_frontier_kernel<<<g, 256, 0, G.stream>>>(a); GB_LAUNCHED();
+    GB_TRY(dalloc(&a.counters, 4, err));
+    CU_TRY(cudaMemsetAsync(a.counters, 0, 32, G.stream), err);
+    const int g = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a.nin, 256 * 4), (int64_t)G.num_sms * 8));
+    push_stats_kernel<<<g, 256, 0, G.stream>>>(a); GB_LAUNCHED();
     unsigned long long h[2] = {0, 0};
     CU_TRY(cudaMemcpyAsync(h, a.counters, 16, cudaMemcpyDeviceToHost, G.stream), err);
     CU_TRY(cudaStreamSynchronize(G.stream), err);
     const int64_t count = (int64_t)h[0], edges = (int64_t)h[1];
-    if (edges * 16 > nnz_total && getenv("B200GRB_FORCE_PUSH") == nullptr) { dfree(a.list); dfree(a.counters); a.list = nullptr; return GrB_SUCCESS; }
+    if (edges * 16 > nnz_total && getenv("B200GRB_FORCE_PUSH") == nullptr) { dfree(a.counters); return GrB_SUCCESS; }
+    GB_TRY(dalloc(&a.list, (size_t)count + 1, err));
+    if (count > 0) {
+        const int gf = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a.nin, 256), (int64_t)G.num_sms * 16));
+        push_frontier_kernel<<<gf, 256, 0, G.stream>>>(a); GB_LAUNCHED();
+    }
     GB_TRY(dalloc(&a.chunk_scan, (size_t)count + 2, err));
     if (count > 0) {
         const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(count + 1, 256), (int64_t)G.num_sms * 16));
