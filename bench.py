@@ -14,7 +14,9 @@ full vector for the next step (strong scaling: the graph is fixed as N grows).
 
 The line also carries the second half of BASELINE.json's metric, SpGEMM Mnnz-out/s, measured
 at N = 1 on configs[3] (R-MAT scale-20 triangle-counting kernel C<L> = L (+.pair) L) under
-"spgemm".
+"spgemm", the full BFS of configs[2] under "bfs" and 16 SSSP sweeps of the configs[4] shape (on the
+scale-22 graph; tools/sssp_bench.py runs scale 24) under "sssp" -- each with its own CPU-port baseline and a
+full-size parity flag.
 
 --impl reference times the CPU side: SuiteSparse:GraphBLAS is not installable offline, so the
 reference arm is the OpenMP port in oracle/grb_fast.c (kind "port") on all host cores, on
@@ -359,9 +361,14 @@ def run_b200(args):
         ok = bool(np.array_equal(pg, p_cpu)) and bool(np.allclose(xg[pg != 0], w_cpu[p_cpu != 0], rtol=2e-5, atol=0))
         out["parity_full_size"] = ok
         if not args.no_spgemm:
-            out["spgemm"] = bench_spgemm(args, torch, stream, gb)
-            out["bfs"] = bench_bfs(args, torch, stream, gb, n, indptr, indices)
-            out["sssp"] = bench_sssp(args, torch, stream, gb, n, indptr, indices)
+            # the other configured workloads (BASELINE.json configs[3], [2], [4]); a failure there must not lose the headline line
+            for key, fn, fargs in (("spgemm", bench_spgemm, (args, torch, stream, gb)),
+                                   ("bfs", bench_bfs, (args, torch, stream, gb, n, indptr, indices)),
+                                   ("sssp", bench_sssp, (args, torch, stream, gb, n, indptr, indices))):
+                try:
+                    out[key] = fn(*fargs)
+                except Exception as e:                      # reported, not hidden
+                    out[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
