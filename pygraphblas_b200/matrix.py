@@ -86,6 +86,25 @@ class Matrix:
         return cls(m)
 
     @classmethod
+    def from_mm(cls, mm_file):
+        """Create a matrix from a Matrix-Market file (matrix.py:377-409 of the reference), parsed in bulk."""
+        from .io import mm_read
+        I, J, V, nrows, ncols, typ = mm_read(mm_file)
+        return cls.from_lists(I, J, V, nrows, ncols, typ)
+
+    def to_mm(self, fileobj):
+        """Write the matrix as a Matrix-Market file (tests/test_matrix.py:329-346 of the reference)."""
+        from .io import mm_write
+        mm_write(self, fileobj)
+
+    @classmethod
+    def from_tsv(cls, tsv_file, typ, nrows, ncols, one_based=True, delimiter="\t"):
+        """(matrix.py:411-475)"""
+        from .io import delimited_read
+        I, J, V = delimited_read(tsv_file, typ, one_based, delimiter)
+        return cls.from_lists(I, J, V, nrows, ncols, typ)
+
+    @classmethod
     def from_scipy(cls, A, typ=None):
         A = A.tocsr()
         A.sort_indices()

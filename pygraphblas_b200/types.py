@@ -73,17 +73,6 @@ _by_handle = {t.gb_type: t for t in ALL_TYPES}
 _promotion_order = (FP64, FP32, INT64, UINT64, INT32, UINT32, INT16, UINT16, INT8, UINT8)
 
 
-def from_python(value):
-    """GraphBLAS type of a Python scalar (types.py:_gb_from_type of the reference: bool, int, float)."""
-    if isinstance(value, (bool, np.bool_)):
-        return BOOL
-    if isinstance(value, (int, np.integer)):
-        return INT64
-    if isinstance(value, (float, np.floating)):
-        return FP64
-    raise TypeError(f"no GraphBLAS type for {type(value).__name__}")
-
-
 def by_name(name):
     return _by_name[name]
 

@@ -1,0 +1,64 @@
+"""CPU: Matrix-Market / delimited-text ingest and egress (pygraphblas_b200/io.py) against the reference's own
+known answers: tests/test_matrix.py:329-357 and the doctest of matrix.py:378-393 (docs/test_mm.mm, whose 12 entries
+are written out below)."""
+import numpy as np
+from pygraphblas_b200 import Matrix, INT8, INT64, FP64, BOOL
+
+TEST_MM = """%%MatrixMarket matrix coordinate integer general
+%%GraphBLAS GrB_INT64
+7 7 12
+1 2 0
+1 4 1
+2 5 2
+2 7 3
+3 6 4
+4 1 5
+4 3 6
+5 6 7
+6 3 8
+7 3 9
+7 4 10
+7 5 11
+"""
+
+
+def test_mm_read_write_known_answers(tmp_path):
+    mmf = tmp_path / "mmwrite_test.mm"
+    m = Matrix.from_lists([0, 1, 2], [0, 1, 2], [2, 3, 4])
+    with mmf.open("w") as f:
+        m.to_mm(f)
+    assert mmf.open().readlines() == ["%%MatrixMarket matrix coordinate integer symmetric\n", "%%GraphBLAS GrB_INT64\n", "3 3 3\n",
+                                      "1 1 2\n", "2 2 3\n", "3 3 4\n"]
+    assert Matrix.from_mm(mmf).iseq(m)
+    p = tmp_path / "test_mm.mm"
+    p.write_text(TEST_MM)
+    M = Matrix.from_mm(p)
+    assert M.type is INT64 and M.shape == (7, 7)
+    assert M.to_lists() == [[0, 0, 1, 1, 2, 3, 3, 4, 5, 6, 6, 6], [1, 3, 4, 6, 5, 0, 2, 5, 2, 2, 3, 4], list(range(12))]
+
+
+def test_mm_symmetric_pattern_real(tmp_path):
+    p = tmp_path / "s.mm"
+    p.write_text("%%MatrixMarket matrix coordinate real symmetric\n% a comment\n3 3 3\n1 1 1.5\n2 1 2.5\n3 2 -1\n")
+    M = Matrix.from_mm(p)
+    assert M.type is FP64 and M.to_lists() == [[0, 0, 1, 1, 2], [0, 1, 0, 2, 1], [1.5, 2.5, 2.5, -1.0, -1.0]]
+    q = tmp_path / "p.mm"
+    q.write_text("%%MatrixMarket matrix coordinate pattern general\n2 3 2\n1 3\n2 1\n")
+    P = Matrix.from_mm(q)
+    assert P.type is BOOL and P.shape == (2, 3) and P.to_lists() == [[0, 1], [2, 0], [True, True]]
+    out = tmp_path / "o.mm"
+    with out.open("w") as f:
+        M.to_mm(f)
+    assert Matrix.from_mm(out).iseq(M)
+    g = Matrix.from_lists([0, 1], [1, 0], [1.0, 2.0], 2, 2, FP64)           # not symmetric: general
+    with out.open("w") as f:
+        g.to_mm(f)
+    assert "general" in out.read_text().splitlines()[0] and Matrix.from_mm(out).iseq(g)
+
+
+def test_tsv_read_known_answer(tmp_path):
+    """tests/test_matrix.py:349-357"""
+    f = tmp_path / "tsv_test.mm"
+    f.write_text("1\t1\t2\n2\t2\t3\n3\t3\t4\n")
+    n = Matrix.from_tsv(f, INT8, 3, 3)
+    assert n.type is INT8 and n.to_lists() == [[0, 1, 2], [0, 1, 2], [2, 3, 4]]
