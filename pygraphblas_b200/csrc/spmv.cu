@@ -7,14 +7,16 @@
 // the matrix type), vectors are dense value arrays + one presence byte per position
 // (no presence array at all when every position is present).
 //
-// Kernel (spmv_tile_kernel): nnz-split, row-segmented.  The nnz range is cut into
-// fixed tiles of SPMV_TILE entries, one CTA per tile, so R-MAT hub rows cannot
-// serialise a warp.  Each thread streams its slice of colidx/values with 128-bit
-// coalesced loads, gathers u[col] (L2-resident), and parks the products in shared
-// memory; the CTA then reduces the row segments that fall inside the tile
-// (thread-per-row for short segments, warp-per-row for long ones).  Rows that
-// straddle tile boundaries leave per-tile head/tail partials that a small fix-up
-// kernel combines in a fixed order -- the result is deterministic for a given matrix.
+// This file: the host logic of both calls (operand casts, kernel choice, write-back) and the tile kernel.
+// Kernel choice, in order:
+//   mask + LOR/LAND/ANY monoid  -> masked push (small frontier, spmv_pull.cu) or masked pull with early exit
+//   nnz >= 4096                 -> run kernel (spmv_run*.cu): 256-entry runs per warp on a cached run plan,
+//                                  compile-time semirings (+ shared-memory hot-column table), run-time
+//                                  operator codes, dense or sparse u
+//   otherwise                   -> tile kernel below: the nnz range is cut into tiles of SPMV_THREADS * items
+//                                  entries, one CTA per tile, item-centric segmented reduction; rows that straddle
+//                                  tiles leave head / tail partials that a fix-up kernel combines in a fixed order.
+// Every path is nnz-split (R-MAT hub rows cannot serialise a warp) and deterministic for a given matrix.
 //
 // Algorithmic bytes per call: nnz*(4 + sizeof(a)) + (nrows+1)*4
 //   + ncols*sizeof(u) + nrows*(sizeof(t) + 1).
