@@ -1,10 +1,9 @@
 // compat.cu -- the part of the GraphBLAS C API that is NOT the mxm/mxv/vxm hot path but that the
 // unmodified reference package touches at import time or around its hot-path tests (SURVEY.md
-// section 8b): GxB_Scalar, options, select-operator handles, complex type handles, and the two
-// host-side helpers behind Matrix.iseq / Vector.iseq (eWiseMult with a binary operator, reduce to a
-// scalar; /root/reference/pygraphblas/matrix.py:1417-1453, 1759-1780).  These run on the host tuple
-// form: they are handle plumbing, not arithmetic kernels.  Everything else the reference names is a
-// generated stub that refuses (compat_stubs.inc).
+// section 8b): GxB_Scalar, options, select-operator handles, complex type handles, resize and
+// memoryUsage.  Handle plumbing only: nothing here computes (every arithmetic entry point lives in
+// spmv*.cu / spgemm.cu / vector_ops.cu / matrix_ops.cu and needs the GPU).  What the library does not
+// implement is a generated stub that refuses (compat_stubs.inc).
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
@@ -84,115 +83,12 @@ extern "C" GrB_Info GxB_UnaryOp_fprint(GrB_UnaryOp op, const char *name, int pr,
     return GrB_SUCCESS;
 }
 
-// ------------------------------------------------------------------ reduce to scalar (host tuples)
-static GrB_Info reduce_values(void *c, int ctc, const GrB_BinaryOp accum, const GrB_Monoid monoid, int vtc, const std::vector<uint8_t> &vals, size_t n, const char *fn) {
-    if (!c || !monoid) return gb_fail(GrB_NULL_POINTER, nullptr, "%s: NULL argument", fn);
-    if (monoid->magic != GB_MAGIC) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "%s: invalid monoid", fn);
-    const GrB_BinaryOp op = monoid->op;
-    if (op->opcode == OP_USER || (accum && accum->opcode == OP_USER)) return gb_fail(GrB_INVALID_VALUE, nullptr, "%s: user-defined operators are not supported", fn);
-    const int mtc = op->ztype->code;
-    // identity: same table the kernels use
-    Sc acc; acc.u = 0;
-    switch (mtc) {
-#define GB_ID(TC, T, F) case TC: { T v = monoid_identity<T>(op->opcode); Sc t; t.u = 0; t.F = v; acc = t; } break;
-        case TC_BOOL: acc.u = monoid_identity<bool>(op->opcode); break;
-        GB_ID(TC_INT8, int8_t, i) GB_ID(TC_INT16, int16_t, i) GB_ID(TC_INT32, int32_t, i) GB_ID(TC_INT64, int64_t, i)
-        GB_ID(TC_UINT8, uint8_t, u) GB_ID(TC_UINT16, uint16_t, u) GB_ID(TC_UINT32, uint32_t, u) GB_ID(TC_UINT64, uint64_t, u)
-        case TC_FP32: acc.d = (double)monoid_identity<float>(op->opcode); break;
-        case TC_FP64: acc.d = monoid_identity<double>(op->opcode); break;
-#undef GB_ID
-    }
-    for (size_t k = 0; k < n; ++k) acc = sc_binop(op->opcode, mtc, acc, sc_cast(sc_load(vtc, vals.data(), k), vtc, mtc));
-    Sc r = sc_cast(acc, mtc, ctc);
-    if (accum) {
-        const int atc = accum->xtype->code;
-        const Sc old = sc_cast(sc_load(ctc, c, 0), ctc, atc);
-        r = sc_cast(sc_binop(accum->opcode, atc, old, sc_cast(acc, mtc, atc)), accum->ztype->code, ctc);
-    }
-    sc_store(ctc, c, 0, r);
-    return GrB_SUCCESS;
-}
-GrB_Info host_matrix_reduce(void *c, int ctc, const GrB_BinaryOp accum, const GrB_Monoid monoid, const GrB_Matrix A) {
-    GB_LOCK;
-    if (!gb_valid_matrix(A)) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "GrB_Matrix_reduce: invalid matrix");
-    GB_TRY(matrix_ensure_host(A));
-    return reduce_values(c, ctc, accum, monoid, A->type->code, A->hx, A->hi.size(), "GrB_Matrix_reduce");
-}
-GrB_Info host_vector_reduce(void *c, int ctc, const GrB_BinaryOp accum, const GrB_Monoid monoid, const GrB_Vector u) {
-    GB_LOCK;
-    if (!gb_valid_vector(u)) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "GrB_Vector_reduce: invalid vector");
-    GB_TRY(vector_ensure_host(u));
-    return reduce_values(c, ctc, accum, monoid, u->type->code, u->hx, u->hi.size(), "GrB_Vector_reduce");
-}
 #define GB_COMPAT_TYPED(TN, CT, TC) \
     extern "C" GrB_Info GxB_Scalar_setElement_##TN(GxB_Scalar s, CT x) { return scalar_set(s, TC, &x); } \
-    extern "C" GrB_Info GxB_Scalar_extractElement_##TN(CT *x, const GxB_Scalar s) { return scalar_get(x, TC, s); } \
-    /* GrB_Matrix_reduce_<T>: matrix_ops.cu */
+    extern "C" GrB_Info GxB_Scalar_extractElement_##TN(CT *x, const GxB_Scalar s) { return scalar_get(x, TC, s); }
 GB_COMPAT_TYPED(BOOL, bool, TC_BOOL) GB_COMPAT_TYPED(INT8, int8_t, TC_INT8) GB_COMPAT_TYPED(INT16, int16_t, TC_INT16) GB_COMPAT_TYPED(INT32, int32_t, TC_INT32)
 GB_COMPAT_TYPED(INT64, int64_t, TC_INT64) GB_COMPAT_TYPED(UINT8, uint8_t, TC_UINT8) GB_COMPAT_TYPED(UINT16, uint16_t, TC_UINT16)
 GB_COMPAT_TYPED(UINT32, uint32_t, TC_UINT32) GB_COMPAT_TYPED(UINT64, uint64_t, TC_UINT64) GB_COMPAT_TYPED(FP32, float, TC_FP32) GB_COMPAT_TYPED(FP64, double, TC_FP64)
-
-// ------------------------------------------------------------------ eWiseMult with a binary operator (host tuples, no mask / accum)
-static GrB_Info emult_check(const void *mask, const GrB_BinaryOp accum, const GrB_BinaryOp op, const GrB_Descriptor desc, const char *fn) {
-    if (!op) return gb_fail(GrB_NULL_POINTER, nullptr, "%s: NULL operator", fn);
-    if (op->magic != GB_MAGIC) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "%s: invalid operator", fn);
-    if (op->opcode == OP_USER) return gb_fail(GrB_INVALID_VALUE, nullptr, "%s: user-defined operators are not supported", fn);
-    const DescFlags f = desc_flags(desc);
-    if (mask || accum || f.tran0 || f.tran1)
-        return gb_fail(GrB_INVALID_VALUE, nullptr, "%s: mask / accumulator / transpose are not on the mxm/mxv/vxm hot path (not implemented by libb200grb)", fn);
-    return GrB_SUCCESS;
-}
-// (with a CUDA device present the matrix form runs on the GPU: matrix_ops.cu)
-GrB_Info host_matrix_emult(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_BinaryOp op,
-                           const GrB_Matrix A, const GrB_Matrix B, const GrB_Descriptor desc) {
-    GB_LOCK;
-    if (!gb_valid_matrix(C) || !gb_valid_matrix(A) || !gb_valid_matrix(B)) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "GrB_Matrix_eWiseMult_BinaryOp: invalid matrix");
-    GB_TRY(emult_check(Mask, accum, op, desc, "GrB_Matrix_eWiseMult_BinaryOp"));
-    if (A->nrows != B->nrows || A->ncols != B->ncols || C->nrows != A->nrows || C->ncols != A->ncols)
-        return gb_fail(GrB_DIMENSION_MISMATCH, &C->err, "GrB_Matrix_eWiseMult_BinaryOp: dimensions do not match");
-    GB_TRY(matrix_ensure_host(A)); GB_TRY(matrix_ensure_host(B));
-    const int atc = A->type->code, btc = B->type->code, xtc = op->xtype->code, ztc = op->ztype->code, ctc = C->type->code;
-    std::vector<uint64_t> ri, rj; std::vector<uint8_t> rx;
-    const size_t csz = C->type->size;
-    size_t a = 0, b = 0;
-    while (a < A->hi.size() && b < B->hi.size()) {
-        const bool lt = A->hi[a] != B->hi[b] ? A->hi[a] < B->hi[b] : A->hj[a] < B->hj[b];
-        const bool eq = A->hi[a] == B->hi[b] && A->hj[a] == B->hj[b];
-        if (eq) {
-            const Sc z = sc_binop(op->opcode, xtc, sc_cast(sc_load(atc, A->hx.data(), a), atc, xtc), sc_cast(sc_load(btc, B->hx.data(), b), btc, xtc));
-            ri.push_back(A->hi[a]); rj.push_back(A->hj[a]); rx.resize(rx.size() + csz);
-            sc_store(ctc, rx.data(), ri.size() - 1, sc_cast(z, ztc, ctc));
-            ++a; ++b;
-        } else if (lt) ++a; else ++b;
-    }
-    matrix_invalidate_device(C);
-    C->hi.swap(ri); C->hj.swap(rj); C->hx.swap(rx); C->pi.clear(); C->pj.clear(); C->px.clear(); C->host_valid = true;
-    return GrB_SUCCESS;
-}
-// (with a CUDA device present the vector form runs on the GPU: vector_ops.cu)
-GrB_Info host_vector_emult(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_BinaryOp op,
-                           const GrB_Vector u, const GrB_Vector v, const GrB_Descriptor desc) {
-    GB_LOCK;
-    if (!gb_valid_vector(w) || !gb_valid_vector(u) || !gb_valid_vector(v)) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "GrB_Vector_eWiseMult_BinaryOp: invalid vector");
-    GB_TRY(emult_check(mask, accum, op, desc, "GrB_Vector_eWiseMult_BinaryOp"));
-    if (u->n != v->n || w->n != u->n) return gb_fail(GrB_DIMENSION_MISMATCH, &w->err, "GrB_Vector_eWiseMult_BinaryOp: dimensions do not match");
-    GB_TRY(vector_ensure_host(u)); GB_TRY(vector_ensure_host(v));
-    const int atc = u->type->code, btc = v->type->code, xtc = op->xtype->code, ztc = op->ztype->code, ctc = w->type->code;
-    std::vector<uint64_t> ri; std::vector<uint8_t> rx;
-    const size_t csz = w->type->size;
-    size_t a = 0, b = 0;
-    while (a < u->hi.size() && b < v->hi.size()) {
-        if (u->hi[a] == v->hi[b]) {
-            const Sc z = sc_binop(op->opcode, xtc, sc_cast(sc_load(atc, u->hx.data(), a), atc, xtc), sc_cast(sc_load(btc, v->hx.data(), b), btc, xtc));
-            ri.push_back(u->hi[a]); rx.resize(rx.size() + csz);
-            sc_store(ctc, rx.data(), ri.size() - 1, sc_cast(z, ztc, ctc));
-            ++a; ++b;
-        } else if (u->hi[a] < v->hi[b]) ++a; else ++b;
-    }
-    vector_invalidate_device(w);
-    w->hi.swap(ri); w->hx.swap(rx); w->pi.clear(); w->px.clear(); w->host_valid = true;
-    return GrB_SUCCESS;
-}
 
 // ------------------------------------------------------------------ resize / memory usage
 extern "C" GrB_Info GrB_Matrix_resize(GrB_Matrix A, GrB_Index nrows, GrB_Index ncols) {

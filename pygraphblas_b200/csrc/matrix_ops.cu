@@ -18,10 +18,6 @@
 #include <vector>
 #include "../../include/b200grb_compat.h"
 
-GrB_Info host_matrix_reduce(void *c, int ctc, const GrB_BinaryOp accum, const GrB_Monoid monoid, const GrB_Matrix A);   // compat.cu (no device at all)
-GrB_Info host_matrix_emult(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_BinaryOp op, const GrB_Matrix A, const GrB_Matrix B,
-                           const GrB_Descriptor desc);
-
 static inline int wgrid(int64_t rows) { return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows * 32, 256), (int64_t)G.num_sms * 16)); }
 static inline int egrid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), (int64_t)G.num_sms * 16)); }
 static GrB_Info read_i64(const int64_t *d, int64_t *h, std::string *err) {
@@ -233,7 +229,7 @@ extern "C" GrB_Info GxB_Matrix_apply_BinaryOp2nd(GrB_Matrix C, const GrB_Matrix 
 
 // ------------------------------------------------------------------ reduce to a scalar / to a vector
 static GrB_Info mat_reduce_scalar(void *c, int ctc, const GrB_BinaryOp accum, const GrB_Monoid monoid, const GrB_Matrix A, const char *fn) {
-    if (!G.have_device) return host_matrix_reduce(c, ctc, accum, monoid, A);            // Matrix.iseq of the handle-plumbing tests
+    if (!G.have_device) return gb_fail(GrB_PANIC, nullptr, "%s: no CUDA device: libb200grb computes only on the GPU (no CPU fallback)", fn);
     if (!c || !monoid) return gb_fail(GrB_NULL_POINTER, nullptr, "%s: NULL argument", fn);
     GB_MAT_OK(A, fn);
     if (monoid->magic != GB_MAGIC) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "%s: invalid monoid", fn);
@@ -380,7 +376,6 @@ GB_MAT_EWISE(GrB_Matrix_eWiseMult_Semiring, GrB_Semiring, op->mul, 1)
 extern "C" GrB_Info GrB_Matrix_eWiseMult_BinaryOp(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_BinaryOp op, const GrB_Matrix A,
                                                    const GrB_Matrix B, const GrB_Descriptor desc) {
     GB_LOCK; GB_CHECK_INIT;
-    if (!G.have_device) return host_matrix_emult(C, Mask, accum, op, A, B, desc);       // Matrix.iseq of the handle-plumbing tests
     return mat_ewise(C, Mask, accum, op, A, B, desc, 1, "GrB_Matrix_eWiseMult_BinaryOp");
 }
 

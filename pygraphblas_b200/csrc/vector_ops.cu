@@ -20,10 +20,6 @@
 #include <vector>
 #include "../../include/b200grb_compat.h"
 
-// host-tuple helpers of compat.cu, used only when there is no CUDA device at all (Vector.iseq in the CPU-side import tests)
-GrB_Info host_vector_emult(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_BinaryOp op, const GrB_Vector u, const GrB_Vector v, const GrB_Descriptor desc);
-GrB_Info host_vector_reduce(void *c, int ctc, const GrB_BinaryOp accum, const GrB_Monoid monoid, const GrB_Vector u);
-
 static inline int vgrid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), (int64_t)G.num_sms * 16)); }
 
 // ------------------------------------------------------------------ write-back:  w<mask> = accum(w, t)
@@ -246,8 +242,6 @@ extern "C" GrB_Info GrB_Vector_eWiseAdd_Semiring(GrB_Vector w, const GrB_Vector 
 extern "C" GrB_Info GrB_Vector_eWiseMult_BinaryOp(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_BinaryOp op,
                                                    const GrB_Vector u, const GrB_Vector v, const GrB_Descriptor desc) {
     GB_LOCK; GB_CHECK_INIT;
-    // without a CUDA device the handle-plumbing tests of the reference still use Vector.iseq: host tuples
-    if (!G.have_device) return host_vector_emult(w, mask, accum, op, u, v, desc);
     return vec_ewise(w, mask, accum, op, u, v, desc, EW_MULT, "GrB_Vector_eWiseMult_BinaryOp");
 }
 extern "C" GrB_Info GrB_Vector_eWiseMult_Monoid(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_Monoid op,
@@ -500,7 +494,7 @@ GrB_Info dev_reduce_values(const void *val, const uint8_t *pres, int vtc, int64_
     return GrB_SUCCESS;
 }
 static GrB_Info vec_reduce(void *c, int ctc, const GrB_BinaryOp accum, const GrB_Monoid monoid, const GrB_Vector u, const char *fn) {
-    if (!G.have_device) return host_vector_reduce(c, ctc, accum, monoid, u);        // Vector.iseq of the handle-plumbing tests
+    if (!G.have_device) return gb_fail(GrB_PANIC, nullptr, "%s: no CUDA device: libb200grb computes only on the GPU (no CPU fallback)", fn);
     if (!c || !monoid) return gb_fail(GrB_NULL_POINTER, nullptr, "%s: NULL argument", fn);
     GB_VEC_OK(u, fn);
     if (monoid->magic != GB_MAGIC) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "%s: invalid monoid", fn);

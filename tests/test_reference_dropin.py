@@ -1,7 +1,7 @@
 """The drop-in boundary, exercised with the UNMODIFIED reference package (CPU container only: the
 reference tree does not travel to the GPU box).  `suitesparse_graphblas/` at the repository root is the
 binding stub of INTEGRATION.md; with it ahead on PYTHONPATH, /root/reference/pygraphblas imports and runs
-on libb200grb.so.  Without a GPU the three hot calls must refuse with Panic ("no CPU fallback") -- never
+on libb200grb.so.  Without a GPU every call that computes must refuse with Panic ("no CPU fallback") -- never
 compute on the host -- while the handle plumbing around them works."""
 import os
 import subprocess
@@ -29,16 +29,16 @@ def test_unmodified_reference_imports_and_plumbing_works():
         m = Matrix.from_lists([0, 1, 2], [1, 2, 0], [1, 2, 3])       # tests/test_matrix.py:250
         assert (m.nrows, m.ncols, m.nvals) == (3, 3, 3) and m.type is INT64
         assert m.to_lists() == [[0, 1, 2], [1, 2, 0], [1, 2, 3]]
-        assert m.iseq(m.dup()) and not m.iseq(Matrix.from_lists([0, 1, 2], [1, 2, 0], [2, 3, 4]))
-        assert m.reduce_int() == 6
+        assert m.dup().to_lists() == m.to_lists()
         v = Vector.from_lists([0, 1, 2], [2, 3, 4])
-        assert v.iseq(v.dup()) and v.to_lists() == [[0, 1, 2], [2, 3, 4]]
+        assert v.dup().to_lists() == [[0, 1, 2], [2, 3, 4]]
         assert INT64.PLUS_TIMES.ztype is INT64 and INT64.min_plus is INT64.MIN_PLUS and BOOL.LOR_LAND.ztype is BOOL
         assert descriptor.T1 in descriptor.CT1 and descriptor.CT1 == (descriptor.C & descriptor.T1)   # tests/test_descriptor.py:6-10
         assert Scalar.from_value(3)[0] == 3
         assert Matrix.sparse(INT64).nrows == 1 << 60                   # matrix.py:167-170
         print("HAVE_DEVICE", lib.B200_have_device())
-        for call in (lambda: m.mxv(v), lambda: v.vxm(m), lambda: m.mxm(m), lambda: m @ m):
+        for call in (lambda: m.mxv(v), lambda: v.vxm(m), lambda: m.mxm(m), lambda: m @ m,
+                     lambda: m.iseq(m.dup()), lambda: m.reduce_int(), lambda: v + v, lambda: m.tril(), lambda: v.apply(INT64.AINV)):
             try:
                 out = call()
                 assert lib.B200_have_device()
@@ -50,15 +50,19 @@ def test_unmodified_reference_imports_and_plumbing_works():
 
 
 def test_reference_own_tests_run_against_the_library():
-    """Run the reference's own unit tests.  Those that only need handle plumbing must pass; the hot-path
-    ones (test_mxm, test_mxv, test_vxm, test_RC, test_RCT0, ...) may fail ONLY with the no-GPU Panic."""
+    """Run the reference's own unit tests.  Those that only need handle plumbing must pass; everything that
+    computes may fail ONLY with the no-GPU Panic (or, for the entry points the library does not implement,
+    with the stub's InvalidValue)."""
     env = dict(os.environ, PYTHONPATH=f"{ROOT}:{REF}")
     files = [f"{REF}/tests/test_{n}.py" for n in ("matrix", "vector", "descriptor", "scalar", "types", "base")]
     r = subprocess.run([sys.executable, "-m", "pytest", "-c", "/dev/null", "--rootdir", "/tmp", "-q", "-p", "no:cacheprovider"] + files,
                        capture_output=True, text=True, env=env, cwd="/tmp", timeout=900)
     out = r.stdout
     passed = int(__import__("re").search(r"(\d+) passed", out).group(1)) if " passed" in out else 0
-    assert passed >= 40, out[-3000:]          # 49 of the reference's 121 tests need nothing beyond the hot path's plumbing
+    assert passed >= 35, out[-3000:]          # 38 of the reference's 121 tests need nothing but handle plumbing
     for line in out.splitlines():
         if line.startswith("FAILED") and any(k in line for k in ("test_mxm", "test_mxv", "test_vxm", "test_RC")):
             assert "Panic" in line, line
+    # nothing computed on the host: every failure is a refusal, not a wrong answer
+    bad = [l for l in out.splitlines() if l.startswith("FAILED") and "AssertionError" in l]
+    assert not bad, bad
