@@ -122,7 +122,13 @@ extern thread_local std::string tl_error;
 
 GrB_Info gb_fail(GrB_Info code, std::string *where, const char *fmt, ...);
 
-#define GB_LOCK std::lock_guard<std::recursive_mutex> _lk(G.mu)
+// every entry point: take the library lock and make the library's device current for the calling host thread
+// (the reference drives `lib` from a ThreadPool, /root/reference/demo/dnn/challenge.py:48-51; a new thread starts on device 0)
+extern thread_local int tl_cuda_device;
+static inline void gb_thread_enter() {
+    if (G.have_device && tl_cuda_device != G.device) { cudaSetDevice(G.device); tl_cuda_device = G.device; }
+}
+#define GB_LOCK std::lock_guard<std::recursive_mutex> _lk(G.mu); gb_thread_enter()
 #define GB_CHECK_INIT  do { if (!G.initialized) return gb_fail(GrB_PANIC, nullptr, "GrB_init not called"); } while (0)
 #define GB_TRY(expr) do { GrB_Info _i = (expr); if (_i != GrB_SUCCESS) return _i; } while (0)
 #define CU_TRY(expr, errstr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) \

@@ -19,6 +19,7 @@
 
 GBGlobal G;
 thread_local std::string tl_error;
+thread_local int tl_cuda_device = -1;
 
 GrB_Info gb_fail(GrB_Info code, std::string *where, const char *fmt, ...) {
     char buf[1024];

@@ -141,3 +141,26 @@ def test_user_defined_operators_are_refused():
     out = Matrix.sparse(FP32, 1, 1)
     # tests/test_udt.py:89-140 style semirings: refused, never run on the CPU
     assert lib.GrB_mxm(out._matrix[0], ffi.NULL, ffi.NULL, sr[0], m._matrix[0], m._matrix[0], ffi.NULL) == lib.GrB_INVALID_VALUE
+
+
+def test_calls_from_a_thread_pool():
+    """The reference drives `lib` from a ThreadPool (demo/dnn/challenge.py:48-51): entry points take the library lock
+    and make the library's device current for the calling thread; distinct objects from distinct threads must work."""
+    from concurrent.futures import ThreadPoolExecutor
+    import pygraphblas_b200 as gb
+    from pygraphblas_b200 import Matrix, Vector
+
+    def work(k):
+        m = Matrix.from_lists([0, 1, 2], [1, 2, 0], [k, k + 1, k + 2])
+        v = Vector.from_lists([0, 2], [k, -k], 3)
+        m[2, 2] = 7
+        assert m.nvals == 4 and v.nvals == 2 and m[0, 1] == k and m.dup().to_lists() == m.to_lists()
+        try:
+            w = m.mxv(v)
+            assert gb.have_device() and w.size == 3
+        except gb.base.Panic:
+            assert not gb.have_device()
+        return k
+
+    with ThreadPoolExecutor(8) as ex:
+        assert sorted(ex.map(work, range(64))) == list(range(64))

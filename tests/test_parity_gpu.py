@@ -399,3 +399,26 @@ def test_sssp_min_plus_matches_scipy():
     fin = np.isfinite(ref)
     assert np.array_equal(np.isfinite(got), fin)
     assert np.allclose(got[fin], ref[fin], rtol=1e-5)
+
+
+def test_hot_calls_from_a_thread_pool():
+    """SURVEY.md 8(b) threading: the reference drives `lib` from a ThreadPool (demo/dnn/challenge.py:48-51); calls
+    on distinct objects from distinct host threads must give the oracle's results."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def work(seed):
+        rng = np.random.default_rng(9000 + seed)
+        typ = util.ALL_T[seed % len(util.ALL_T)]
+        A = util.rand_mat(rng, typ, 40, 30, 0.2)
+        u = util.rand_vec(rng, typ, 30, 0.7)
+        w = util.rand_vec(rng, typ, 40, 0.3)
+        sr = util.semirings_for(typ)[seed % 5]
+        case = {"op": "mxv", "A": A, "u": u, "w": w, "mask": None, "accum": None, "semiring": list(sr), "desc": ""}
+        _check(case, util.product_run(case))
+        B = util.rand_mat(rng, typ, 30, 20, 0.2)
+        case = {"op": "mxm", "A": A, "B": B, "C": util.rand_mat(rng, typ, 40, 20, 0.1), "mask": None, "accum": None, "semiring": list(sr), "desc": ""}
+        _check(case, util.product_run(case))
+        return seed
+
+    with ThreadPoolExecutor(8) as ex:
+        assert sorted(ex.map(work, range(48))) == list(range(48))
