@@ -66,3 +66,35 @@ def test_reference_own_tests_run_against_the_library():
     # nothing computed on the host: every failure is a refusal, not a wrong answer
     bad = [l for l in out.splitlines() if l.startswith("FAILED") and "AssertionError" in l]
     assert not bad, bad
+
+
+def test_slice_to_index_list_matches_the_reference():
+    """Vector._index (the mirror) against the reference's own base._build_range (base.py:216-252) on a grid of
+    slices and lists: same GrB_ALL / GxB_RANGE / GxB_STRIDE / GxB_BACKWARDS encoding, same result length."""
+    r = _run("""
+        import itertools
+        import pygraphblas as ref
+        from pygraphblas.base import _build_range, lib as rlib, ffi as rffi
+        import pygraphblas_b200 as gb
+        v = gb.Vector.sparse(gb.INT64, 10)
+        vals = [None, 0, 1, 3, 8, 9]
+        steps = [None, 1, 2, 3, -1, -2, -3]
+        n = 0
+        for a, b, c in itertools.product(vals, vals, steps):
+            sl = slice(a, b, c)
+            I0, ni0, sz0 = _build_range(sl, 9)
+            I1, ni1, sz1 = v._index(sl, 10)
+            if I0 == rlib.GrB_ALL:
+                assert I1 == gb.lib.GrB_ALL and sz1 == 10, (sl,)
+                continue
+            assert int(ni0) == int(ni1), (sl, ni0, ni1)
+            k = 2 if int(ni0) == int(rlib.GxB_RANGE) else 3
+            assert [int(I0[q]) for q in range(k)] == [int(I1[q]) for q in range(k)], sl
+            assert sz0 == sz1, (sl, sz0, sz1)
+            n += 1
+        I0, ni0, sz0 = _build_range([2, 3, 5, 7], 9)
+        I1, ni1, sz1 = v._index([2, 3, 5, 7], 10)
+        assert (ni0, sz0) == (ni1, sz1) == (4, 4) and [int(I1[q]) for q in range(4)] == I0
+        print("OK", n)
+    """)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
