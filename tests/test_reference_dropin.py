@@ -98,3 +98,29 @@ def test_slice_to_index_list_matches_the_reference():
         print("OK", n)
     """)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_type_promotion_and_default_operators_match_the_reference():
+    """types.promote (types.py:484-500), the default semiring / add / mult operators per type (types.py:156-160)
+    and every semiring's ztype, mirror against the reference's own objects."""
+    r = _run("""
+        import pygraphblas as ref
+        import pygraphblas_b200 as gb
+        names = ["BOOL", "INT8", "INT16", "INT32", "INT64", "UINT8", "UINT16", "UINT32", "UINT64", "FP32", "FP64"]
+        for a in names:
+            for b in names:
+                assert ref.types.promote(getattr(ref, a), getattr(ref, b)).__name__ == gb.types.promote(getattr(gb, a), getattr(gb, b)).name, (a, b)
+            ra, ga = getattr(ref, a), getattr(gb, a)
+            assert ra._default_semiring().name == ga._default_semiring().name, a
+            assert ra._default_addop().name == ga._default_addop().name and ra._default_multop().name == ga._default_multop().name, a
+        n = 0
+        for name, sr in gb.ops.semirings.items():
+            rs = getattr(getattr(ref, sr.type), f"{sr.pls}_{sr.mul}", None)
+            if rs is None:
+                continue
+            assert rs.ztype.__name__ == sr.ztype.name, name
+            n += 1
+        assert n > 1000, n
+        print("OK", n)
+    """)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
