@@ -12,7 +12,7 @@ import numpy as np
 
 from .base import lib, ffi, NULL, _check, NoValue
 from . import types
-from .ops import current_semiring, current_accum
+from .ops import current_semiring, current_accum, current_binop, current_monoid, get_bin_op
 from .descriptor import current_desc, T0 as _T0
 
 GxB_INDEX_MAX = 1 << 60
@@ -360,18 +360,26 @@ class Matrix:
         """(matrix.py:1965-2005)"""
         if out is None:
             out = Matrix.sparse(self.type, self.nrows, self.ncols)
-        typ = types.from_python(first)
+        from .scalar import Scalar
         mask, accum, desc = self._get_args(mask, accum, desc)
-        _check(typ._Matrix_apply_BinaryOp1st(out._matrix[0], mask, accum, op.get_op(), typ.from_value(first), self._matrix[0], desc))
+        if isinstance(first, Scalar):
+            self._keep = first
+            _check(lib.GxB_Matrix_apply_BinaryOp1st(out._matrix[0], mask, accum, op.get_op(), first._scalar[0], self._matrix[0], desc))
+        else:           # the typed entry point of the matrix's own type (matrix.py:1992-2005)
+            _check(self.type._Matrix_apply_BinaryOp1st(out._matrix[0], mask, accum, op.get_op(), first, self._matrix[0], desc))
         return out
 
     def apply_second(self, op, second, out=None, mask=None, accum=None, desc=None):
         """(matrix.py:2007-2040)"""
         if out is None:
             out = Matrix.sparse(self.type, self.nrows, self.ncols)
-        typ = types.from_python(second)
+        from .scalar import Scalar
         mask, accum, desc = self._get_args(mask, accum, desc)
-        _check(typ._Matrix_apply_BinaryOp2nd(out._matrix[0], mask, accum, op.get_op(), self._matrix[0], typ.from_value(second), desc))
+        if isinstance(second, Scalar):
+            self._keep = second
+            _check(lib.GxB_Matrix_apply_BinaryOp2nd(out._matrix[0], mask, accum, op.get_op(), self._matrix[0], second._scalar[0], desc))
+        else:           # matrix.py:2027-2040
+            _check(self.type._Matrix_apply_BinaryOp2nd(out._matrix[0], mask, accum, op.get_op(), self._matrix[0], second, desc))
         return out
 
     def pattern(self, typ=types.BOOL, out=None):
@@ -391,7 +399,7 @@ class Matrix:
         if out is None:
             out = Matrix.sparse(cast or types.promote(self.type, other.type), self.nrows, self.ncols)
         if add_op is None:
-            add_op = out.type._default_addop()
+            add_op = current_binop.get(None) or out.type._default_addop()
         mask, accum, desc = self._get_args(mask, accum, desc)
         _check(func(out._matrix[0], mask, accum, add_op.get_op(), self._matrix[0], other._matrix[0], desc))
         return out
@@ -401,14 +409,16 @@ class Matrix:
         if out is None:
             out = Matrix.sparse(cast or types.promote(self.type, other.type), self.nrows, self.ncols)
         if mult_op is None:
-            mult_op = out.type._default_multop()
+            mult_op = current_binop.get(None) or out.type._default_multop()
+        elif isinstance(mult_op, str):
+            mult_op = get_bin_op(mult_op, self.type)
         mask, accum, desc = self._get_args(mask, accum, desc)
         _check(lib.GrB_Matrix_eWiseMult_BinaryOp(out._matrix[0], mask, accum, mult_op.get_op(), self._matrix[0], other._matrix[0], desc))
         return out
 
     def _reduce(self, typ, mon, accum=None):
         if mon is None:
-            mon = getattr(typ, "LOR_MONOID" if typ is types.BOOL else "PLUS_MONOID")
+            mon = current_monoid.get(None) or getattr(typ, "LOR_MONOID" if typ is types.BOOL else "PLUS_MONOID")
         x = ffi.new(typ.ptr)
         _, accum, desc = self._get_args(None, accum, None)
         _check(typ._Matrix_reduce(x, accum, mon.get_op(), self._matrix[0], desc))
@@ -438,28 +448,82 @@ class Matrix:
         _check(lib.GrB_Matrix_reduce_Monoid(out._vector[0], mask, accum, mon.get_op(), self._matrix[0], desc))
         return out
 
-    def _scalar_or_matrix(self, other, mat_fn, op, first=False):
-        if isinstance(other, Matrix):
-            return mat_fn(other, op)
-        return self.apply_first(other, op) if first else self.apply_second(op, other)
+    # arithmetic operators: exactly the calls the reference makes (matrix.py:1625-1720), including the default
+    # operator taken from the `with <BinaryOp>:` context and the operand order of the in-place forms
+    def __and__(self, other):
+        return self.emult(other, current_binop.get(self.type.SECOND))
 
-    def __add__(self, o):
-        return self._scalar_or_matrix(o, self.eadd, self.type.PLUS)
+    def __iand__(self, other):
+        return self.emult(other, current_binop.get(self.type.SECOND), out=self)
 
-    def __sub__(self, o):
-        return self._scalar_or_matrix(o, self.eadd, self.type.MINUS)
+    def __or__(self, other):
+        return self.eadd(other, current_binop.get(self.type.SECOND))
 
-    def __mul__(self, o):
-        return self._scalar_or_matrix(o, self.emult, self.type.TIMES)
+    def __ior__(self, other):
+        return self.eadd(other, current_binop.get(self.type.SECOND), out=self)
 
-    def __truediv__(self, o):
-        return self._scalar_or_matrix(o, self.emult, self.type.DIV)
+    def __add__(self, other):
+        op = current_binop.get(self.type.PLUS)
+        if not isinstance(other, Matrix):
+            return self.apply_second(op, other)
+        return self.eadd(other, op)
 
-    def __or__(self, o):
-        return self.eadd(o)
+    def __radd__(self, other):
+        return self.apply_first(other, current_binop.get(self.type.PLUS))
 
-    def __and__(self, o):
-        return self.emult(o)
+    def __iadd__(self, other):
+        op = current_binop.get(self.type.PLUS)
+        if not isinstance(other, Matrix):
+            return self.apply_second(op, other, out=self)
+        return self.eadd(other, op, out=self)
+
+    def __sub__(self, other):
+        op = current_binop.get(self.type.MINUS)
+        if not isinstance(other, Matrix):
+            return self.apply_second(op, other)
+        return self.eadd(other, op)
+
+    def __rsub__(self, other):
+        return self.apply_first(other, current_binop.get(self.type.MINUS))
+
+    def __isub__(self, other):
+        op = current_binop.get(self.type.MINUS)
+        if not isinstance(other, Matrix):
+            return self.apply_second(op, other, out=self)
+        return other.eadd(self, op, out=self)
+
+    def __mul__(self, other):
+        op = current_binop.get(self.type.TIMES)
+        if not isinstance(other, Matrix):
+            return self.apply_second(op, other)
+        return self.emult(other, op)
+
+    def __rmul__(self, other):
+        return self.apply_first(other, current_binop.get(self.type.TIMES))
+
+    def __imul__(self, other):
+        op = current_binop.get(self.type.TIMES)
+        if not isinstance(other, Matrix):
+            return self.apply_second(op, other)
+        return other.emult(self, op, out=self)
+
+    def __truediv__(self, other):
+        op = current_binop.get(self.type.DIV)
+        if not isinstance(other, Matrix):
+            return self.apply_second(op, other)
+        return self.emult(other, op)
+
+    def __rtruediv__(self, other):
+        return self.apply_first(other, current_binop.get(self.type.DIV))
+
+    def __itruediv__(self, other):
+        op = current_binop.get(self.type.DIV)
+        if not isinstance(other, Matrix):
+            return self.apply_second(op, other)
+        return other.emult(self, op, out=self)
+
+    def __invert__(self):
+        return self.apply(self.type.MINV)
 
     def __neg__(self):
         return self.apply(self.type.AINV)

@@ -12,6 +12,8 @@ from . import types
 
 current_semiring = contextvars.ContextVar("current_semiring")
 current_accum = contextvars.ContextVar("current_accum")
+current_binop = contextvars.ContextVar("current_binop")        # binaryop.py:18 of the reference
+current_monoid = contextvars.ContextVar("current_monoid")      # monoid.py:16
 
 _T = "BOOL|UINT8|UINT16|UINT32|UINT64|INT8|INT16|INT32|INT64|FP32|FP64"
 
@@ -20,6 +22,17 @@ class BinaryOp:
     def __init__(self, op, typ, handle):
         self.op, self.type, self.binaryop = op, typ, handle
         self.name = f"{op}_{typ}"
+
+    def __enter__(self):                            # `with INT64.MAX: c = a | b`  (binaryop.py:51-57)
+        self.token = current_binop.set(self)
+        return self
+
+    def __exit__(self, *errors):
+        current_binop.reset(self.token)
+        return False
+
+    def __call__(self, A, B, *args, **kwargs):      # binaryop.py:59-60
+        return A.emult(B, self, *args, **kwargs)
 
     def get_op(self):
         return self.binaryop
@@ -64,6 +77,14 @@ class Monoid:
     def __init__(self, op, typ, handle):
         self.op, self.type, self.monoid = op, typ, handle
         self.name = f"{op}_{typ}_MONOID"
+
+    def __enter__(self):                            # `with INT8.TIMES_MONOID: m.reduce_int()`  (monoid.py:60-66)
+        self.token = current_monoid.set(self)
+        return self
+
+    def __exit__(self, *errors):
+        current_monoid.reset(self.token)
+        return False
 
     def get_op(self):
         return self.monoid
@@ -111,6 +132,14 @@ class Semiring:
 
     def __repr__(self):
         return f"<Semiring {self.name}>"
+
+
+_STR_BINOP = {">": "GT", "<": "LT", ">=": "GE", "<=": "LE", "!=": "NE", "==": "EQ", "+": "PLUS", "-": "MINUS", "*": "TIMES", "/": "DIV"}
+
+
+def get_bin_op(op, typ):
+    """'+', '>=' ... -> the operator of `typ` (base.py:270-282)."""
+    return getattr(typ, _STR_BINOP[op])
 
 
 _binop_re = re.compile(rf"^(?:GrB|GxB)_([A-Z0-9]+)_({_T})$")

@@ -7,14 +7,14 @@ import numpy as np
 
 from .base import lib, ffi, NULL, _check, NoValue
 from . import types
-from .ops import current_semiring, current_accum
+from .ops import current_semiring, current_accum, current_binop, current_monoid, get_bin_op
 from .descriptor import current_desc, T1 as _T1
 
 GxB_INDEX_MAX = 1 << 60
 
 
 class Vector:
-    __slots__ = ("_vector", "_mask_alive", "__weakref__")
+    __slots__ = ("_vector", "_mask_alive", "_keep_scalar", "__weakref__")
 
     def __init__(self, handle):
         self._vector = handle
@@ -250,7 +250,7 @@ class Vector:
             func = lib.GrB_Vector_eWiseAdd_Semiring
         out = self._out_like(out, cast or types.promote(self.type, other.type))
         if add_op is None:
-            add_op = out.type._default_addop()
+            add_op = current_binop.get(None) or out.type._default_addop()
         mask, accum, desc = self._get_args(mask, accum, desc)
         _check(func(out._vector[0], mask, accum, add_op.get_op(), self._vector[0], other._vector[0], desc))
         return out
@@ -259,7 +259,9 @@ class Vector:
         """Element-wise intersection w<mask> = accum(w, u (x) v)  (vector.py:737-833; also `&`, `*`, `/`)."""
         out = self._out_like(out, cast or types.promote(self.type, other.type))
         if mult_op is None:
-            mult_op = out.type._default_multop()
+            mult_op = current_binop.get(None) or out.type._default_multop()
+        elif isinstance(mult_op, str):
+            mult_op = get_bin_op(mult_op, self.type)
         mask, accum, desc = self._get_args(mask, accum, desc)
         _check(lib.GrB_Vector_eWiseMult_BinaryOp(out._vector[0], mask, accum, mult_op.get_op(), self._vector[0], other._vector[0], desc))
         return out
@@ -273,18 +275,26 @@ class Vector:
 
     def apply_first(self, first, op, out=None, mask=None, accum=None, desc=None):
         """w = op(first, u)  (vector.py:1131-1153)."""
+        from .scalar import Scalar
         out = self._out_like(out)
-        typ = types.from_python(first)
         mask, accum, desc = self._get_args(mask, accum, desc)
-        _check(typ._Vector_apply_BinaryOp1st(out._vector[0], mask, accum, op.get_op(), typ.from_value(first), self._vector[0], desc))
+        if isinstance(first, Scalar):
+            self._keep_scalar = first
+            _check(lib.GxB_Vector_apply_BinaryOp1st(out._vector[0], mask, accum, op.get_op(), first._scalar[0], self._vector[0], desc))
+        else:           # the typed entry point of the vector's own type, as the reference picks it (vector.py:1293-1299)
+            _check(self.type._Vector_apply_BinaryOp1st(out._vector[0], mask, accum, op.get_op(), first, self._vector[0], desc))
         return out
 
     def apply_second(self, op, second, out=None, mask=None, accum=None, desc=None):
         """w = op(u, second)  (vector.py:1155-1178)."""
+        from .scalar import Scalar
         out = self._out_like(out)
-        typ = types.from_python(second)
         mask, accum, desc = self._get_args(mask, accum, desc)
-        _check(typ._Vector_apply_BinaryOp2nd(out._vector[0], mask, accum, op.get_op(), self._vector[0], typ.from_value(second), desc))
+        if isinstance(second, Scalar):
+            self._keep_scalar = second
+            _check(lib.GxB_Vector_apply_BinaryOp2nd(out._vector[0], mask, accum, op.get_op(), self._vector[0], second._scalar[0], desc))
+        else:           # vector.py:1345-1351
+            _check(self.type._Vector_apply_BinaryOp2nd(out._vector[0], mask, accum, op.get_op(), self._vector[0], second, desc))
         return out
 
     def _index(self, index, dim):
@@ -331,7 +341,7 @@ class Vector:
 
     def _reduce(self, typ, mon, accum=None):
         if mon is None:
-            mon = getattr(typ, "LOR_MONOID" if typ is types.BOOL else "PLUS_MONOID")
+            mon = current_monoid.get(None) or getattr(typ, "LOR_MONOID" if typ is types.BOOL else "PLUS_MONOID")
         x = ffi.new(typ.ptr)
         mask, accum, desc = self._get_args(None, accum, None)
         _check(typ._Vector_reduce(x, accum, mon.get_op(), self._vector[0], desc))
@@ -352,75 +362,108 @@ class Vector:
     def pattern(self, typ=types.BOOL):
         """(vector.py:1405-1414)"""
         out = Vector.sparse(typ, self.size)
-        self.apply(typ.ONE, out=out)
+        self.apply(types.BOOL.ONE, out=out)
         return out
 
-    def _scalar_or_vector(self, other, vec_fn, op, first=False):
-        if isinstance(other, Vector):
-            return vec_fn(other, op)
-        return self.apply_first(other, op) if first else self.apply_second(op, other)
+    # arithmetic operators: exactly the calls the reference makes (vector.py:991-1063), operand order of the
+    # in-place forms included (`a -= b` evaluates MINUS(b, a) on the intersection there, :1016-1019)
+    def __add__(self, other):
+        if not isinstance(other, Vector):
+            return self.apply_second(self.type.PLUS, other)
+        return self.eadd(other)
 
-    def __add__(self, o):
-        return self._scalar_or_vector(o, self.eadd, self.type.PLUS)
+    def __radd__(self, other):
+        return self.apply_first(other, self.type.PLUS)
 
-    def __radd__(self, o):
-        return self._scalar_or_vector(o, self.eadd, self.type.PLUS, first=True)
+    def __iadd__(self, other):
+        if not isinstance(other, Vector):
+            return self.apply_second(self.type.PLUS, other, out=self)
+        return self.eadd(other, out=self)
 
-    def __sub__(self, o):
-        return self._scalar_or_vector(o, self.eadd, self.type.MINUS)
+    def __sub__(self, other):
+        if not isinstance(other, Vector):
+            return self.apply_second(self.type.MINUS, other)
+        return self.eadd(other, self.type.MINUS)
 
-    def __rsub__(self, o):
-        return self._scalar_or_vector(o, self.eadd, self.type.MINUS, first=True)
+    def __rsub__(self, other):
+        return self.apply_first(other, self.type.MINUS)
 
-    def __mul__(self, o):
-        return self._scalar_or_vector(o, self.emult, self.type.TIMES)
+    def __isub__(self, other):
+        if not isinstance(other, Vector):
+            return self.apply_second(self.type.MINUS, other)
+        return other.eadd(self, self.type.MINUS, out=self)
 
-    def __rmul__(self, o):
-        return self._scalar_or_vector(o, self.emult, self.type.TIMES, first=True)
+    def __mul__(self, other):
+        if not isinstance(other, Vector):
+            return self.apply_second(self.type.TIMES, other)
+        return self.emult(other, self.type.TIMES)
 
-    def __truediv__(self, o):
-        return self._scalar_or_vector(o, self.emult, self.type.DIV)
+    def __rmul__(self, other):
+        return self.apply_first(other, self.type.TIMES)
 
-    def _inplace(self, other, vec_fn, op):
-        if isinstance(other, Vector):
-            return vec_fn(other, op, out=self)
-        return self.apply_second(op, other, out=self)
+    def __imul__(self, other):
+        if not isinstance(other, Vector):
+            return self.apply_second(self.type.TIMES, other, out=self)
+        return other.emult(self, self.type.TIMES, out=self)
 
-    def __iadd__(self, o):
-        return self._inplace(o, self.eadd, self.type.PLUS)
+    def __truediv__(self, other):
+        if not isinstance(other, Vector):
+            return self.apply_second(self.type.DIV, other)
+        return self.emult(other, self.type.DIV)
 
-    def __isub__(self, o):
-        return self._inplace(o, self.eadd, self.type.MINUS)
+    def __rtruediv__(self, other):
+        return self.apply_first(other, self.type.DIV)
 
-    def __imul__(self, o):
-        return self._inplace(o, self.emult, self.type.TIMES)
+    def __itruediv__(self, other):
+        if not isinstance(other, Vector):
+            return self.apply_second(self.type.DIV, other, out=self)
+        return other.emult(self, self.type.DIV, out=self)
 
-    def __itruediv__(self, o):
-        return self._inplace(o, self.emult, self.type.DIV)
+    def __and__(self, other):
+        return self.emult(other)
 
-    def __rtruediv__(self, o):
-        return self.apply_first(o, self.type.DIV)
+    def __iand__(self, other):
+        return self.emult(other, out=self)
 
-    def __ior__(self, o):
-        return self.eadd(o, out=self)
+    def __or__(self, other):
+        return self.eadd(other)
 
-    def __iand__(self, o):
-        return self.emult(o, out=self)
+    def __ior__(self, other):
+        return self.eadd(other, out=self)
 
     def __invert__(self):
         return self.apply(self.type.MINV)
-
-    def __or__(self, o):
-        return self.eadd(o)
-
-    def __and__(self, o):
-        return self.emult(o)
 
     def __neg__(self):
         return self.apply(self.type.AINV)
 
     def __abs__(self):
         return self.apply(self.type.ABS)
+
+    _SELECT = {">": "GT_THUNK", "<": "LT_THUNK", ">=": "GE_THUNK", "<=": "LE_THUNK", "!=": "NE_THUNK", "==": "EQ_THUNK",
+               ">0": "GT_ZERO", "<0": "LT_ZERO", ">=0": "GE_ZERO", "<=0": "LE_ZERO", "!=0": "NONZERO", "==0": "EQ_ZERO"}
+
+    def select(self, op, thunk=None, out=None, mask=None, accum=None, desc=None):
+        """w<mask> = accum(w, select(u, thunk))  (vector.py:1361-1403)."""
+        from .scalar import Scalar
+        if out is None:
+            out = Vector.sparse(self.type, self.size)
+        if isinstance(op, str):
+            op = getattr(lib, "GxB_" + self._SELECT[op])
+        keep = None
+        if thunk is None:
+            thunk = NULL
+        elif isinstance(thunk, (bool, int, float)):
+            keep = Scalar.from_value(thunk); thunk = keep._scalar[0]
+        elif isinstance(thunk, Scalar):
+            keep = thunk; thunk = keep._scalar[0]
+        mask, accum, desc = self._get_args(mask, accum, desc)
+        _check(lib.GxB_Vector_select(out._vector[0], mask, accum, op, self._vector[0], thunk, desc))
+        return out
+
+    def nonzero(self):
+        """(vector.py:1426-1428)"""
+        return self.select(lib.GxB_NONZERO)
 
     def __matmul__(self, other):
         from .matrix import Matrix

@@ -223,3 +223,80 @@ def test_output_inference_of_the_hot_calls_matches_the_reference():
         print("OK", n)
     """)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+FFI_CASES = r'''
+MASKS={}
+v=lambda p,t="INT64": p.Vector.from_lists([0,2,5],[1,2,3],8,getattr(p,t))
+w=lambda p,t="INT64": p.Vector.from_lists([0,1,2,6],[1,2,3,4],8,getattr(p,t))
+m=lambda p,t="INT64": p.Matrix.from_lists([0,1,2],[1,2,0],[1,2,3],4,4,getattr(p,t))
+m2=lambda p,t="INT64": p.Matrix.from_lists([0,1,2,3,3],[1,2,0,0,3],[1,2,3,4,5],4,4,getattr(p,t))
+bmask=lambda p: p.Vector.from_lists([0,2],[True,False],8,p.BOOL)
+cases={
+ "eadd": lambda p: v(p).eadd(w(p)), "eadd_max": lambda p: v(p).eadd(w(p), p.INT64.MAX), "eadd_mon": lambda p: v(p).eadd(w(p), p.INT64.PLUS_MONOID),
+ "or": lambda p: v(p) | w(p), "add": lambda p: v(p) + w(p), "sub": lambda p: v(p) - w(p), "mul": lambda p: v(p) * w(p), "div": lambda p: v(p) / w(p),
+ "and": lambda p: v(p) & w(p), "emult": lambda p: v(p).emult(w(p)), "emult_mixed": lambda p: v(p,"FP32").emult(v(p,"INT8")),
+ "apply": lambda p: v(p).apply(p.INT64.AINV), "neg": lambda p: -v(p), "abs": lambda p: abs(v(p)), "inv": lambda p: ~v(p,"FP64"),
+ "first": lambda p: v(p).apply_first(2, p.INT64.PLUS), "second": lambda p: v(p).apply_second(p.INT64.MINUS, 2),
+ "add3": lambda p: v(p) + 3, "radd3": lambda p: 3 + v(p), "rsub": lambda p: 3 - v(p), "sub3": lambda p: v(p) - 3, "mul3": lambda p: v(p) * 3, "rmul": lambda p: 3 * v(p),
+ "div3": lambda p: v(p) / 3, "rdiv": lambda p: 15 / v(p), "mulf": lambda p: v(p,"FP64") * 2.5,
+ "iadd": lambda p: v(p).__iadd__(3), "iaddv": lambda p: v(p).__iadd__(w(p)), "isub": lambda p: v(p).__isub__(3), "isubv": lambda p: v(p).__isub__(w(p)),
+ "imul": lambda p: v(p).__imul__(3), "imulv": lambda p: v(p).__imul__(w(p)), "idiv": lambda p: v(p).__itruediv__(3), "idivv": lambda p: v(p).__itruediv__(w(p)),
+ "ior": lambda p: v(p).__ior__(w(p)), "iand": lambda p: v(p).__iand__(w(p)),
+ "assign_scalar": lambda p: v(p).assign_scalar(3), "assign_scalar_f": lambda p: v(p).assign_scalar(2.5), "assign_scalar_mask": lambda p: v(p,"UINT8").assign_scalar(2, mask=MASKS.setdefault(p.__name__, bmask(p))),
+ "setall": lambda p: v(p).__setitem__(slice(None), 3), "setslice": lambda p: v(p).__setitem__(slice(2,7), 1), "setmask": lambda p: v(p).__setitem__(MASKS.setdefault(p.__name__, bmask(p)), 4),
+ "setvec": lambda p: v(p).__setitem__(slice(None), w(p)), "assign": lambda p: v(p).assign(w(p)), "getslice": lambda p: v(p)[1:5], "getstride": lambda p: v(p)[7:1:-2], "getlist": lambda p: v(p)[[2,3,5]],
+ "reduce_int": lambda p: v(p).reduce_int(), "reduce_bool": lambda p: p.Vector.from_lists([0,2],[True,False],8,p.BOOL).reduce_bool(), "reduce_float": lambda p: v(p,"FP64").reduce_float(), "reduce_int_mon": lambda p: v(p).reduce_int(p.INT64.MAX_MONOID),
+ "pattern": lambda p: v(p).pattern(), "pattern8": lambda p: v(p).pattern(p.INT8),
+ "nonzero": lambda p: v(p).nonzero(), "select_gt": lambda p: v(p).select(">", 1),
+ "m_tril": lambda p: m(p).tril(), "m_triu1": lambda p: m(p).triu(1), "m_offdiag": lambda p: m(p).offdiag(), "m_nonzero": lambda p: m(p).nonzero(),
+ "m_select_gt": lambda p: m(p).select(">", 2), "m_select_op": lambda p: m(p).select(p.lib.GxB_TRIL, -1),
+ "m_apply": lambda p: m(p).apply(p.INT64.ABS), "m_neg": lambda p: -m(p), "m_first": lambda p: m(p).apply_first(2, p.INT64.PLUS), "m_second": lambda p: m(p).apply_second(p.INT64.TIMES, 3),
+ "m_reduce_int": lambda p: m(p).reduce_int(), "m_reduce_float": lambda p: m(p,"FP64").reduce_float(), "m_reduce_bool": lambda p: p.Matrix.from_lists([0,1],[1,0],[True,False],4,4,p.BOOL).reduce_bool(), "m_reduce_vector": lambda p: m(p).reduce_vector(),
+ "m_reduce_vector_T0": lambda p: m(p).reduce_vector(desc=p.descriptor.T0),
+ "m_eadd": lambda p: m(p).eadd(m2(p)), "m_add": lambda p: m(p) + m2(p), "m_sub": lambda p: m(p) - m2(p), "m_emult": lambda p: m(p).emult(m2(p)), "m_mul": lambda p: m(p) * m2(p), "m_div": lambda p: m(p) / m2(p),
+ "m_or": lambda p: m(p) | m2(p), "m_and": lambda p: m(p) & m2(p), "m_pattern": lambda p: m(p).pattern(), "m_add3": lambda p: m(p) + 3, "m_mul3": lambda p: m(p) * 3,
+ "m_iadd": lambda p: m(p).__iadd__(m2(p)), "m_isub": lambda p: m(p).__isub__(m2(p)), "m_imul": lambda p: m(p).__imul__(m2(p)), "m_idiv": lambda p: m(p).__itruediv__(m2(p)), "m_ior": lambda p: m(p).__ior__(m2(p)), "m_iand": lambda p: m(p).__iand__(m2(p)), "m_iadd3": lambda p: m(p).__iadd__(3), "m_isub3": lambda p: m(p).__isub__(3), "m_imul3": lambda p: m(p).__imul__(3), "m_idiv3": lambda p: m(p).__itruediv__(3), "m_radd": lambda p: 3 + m(p), "m_rsub": lambda p: 3 - m(p), "m_rmul": lambda p: 3 * m(p), "m_rdiv": lambda p: 12 / m(p), "m_inv": lambda p: ~m(p,"FP64"), "m_abs": lambda p: abs(m(p)),
+ "m_transpose": lambda p: m(p).transpose(), "m_T": lambda p: m(p).T,
+}
+
+cases.update({
+ # operators taken from context managers, string operators, Scalar operands, masks / accumulators / descriptors
+ "ctx_binop": lambda p: _with(p.INT64.MAX, lambda: v(p) | w(p)), "ctx_binop_m": lambda p: _with(p.INT64.MIN, lambda: m(p) + m2(p)),
+ "ctx_monoid": lambda p: _with(p.INT64.TIMES_MONOID, lambda: v(p).reduce_int()), "ctx_monoid_m": lambda p: _with(p.FP64.MAX_MONOID, lambda: m(p, "FP64").reduce_float()),
+ "ctx_accum": lambda p: _with(p.Accum(p.INT64.MIN), lambda: v(p).eadd(w(p), out=v(p))),
+ "str_op": lambda p: v(p).emult(w(p), "+"), "str_op2": lambda p: m(p).emult(m2(p), ">="),
+ "scalar_first": lambda p: v(p).apply_first(MASKS.setdefault(p.__name__ + "s", p.Scalar.from_value(2)), p.INT8.PLUS),
+ "scalar_second": lambda p: m(p).apply_second(p.INT8.MINUS, MASKS.setdefault(p.__name__ + "s", p.Scalar.from_value(2))),
+ "eadd_full": lambda p: v(p).eadd(w(p), p.INT64.MIN, out=w(p), mask=MASKS.setdefault(p.__name__ + "2", bmask(p)), accum=p.INT64.PLUS, desc=p.descriptor.RSC),
+ "m_eadd_T": lambda p: m(p).eadd(m2(p), p.INT64.MAX, desc=p.descriptor.T0T1), "m_select_desc": lambda p: m(p).select("<", 3, desc=p.descriptor.T0),
+ "cast": lambda p: v(p).eadd(w(p), cast=p.FP32), "m_cast": lambda p: m(p).emult(m2(p, "FP32"), cast=p.FP64),
+})
+'''
+
+
+def test_every_operation_makes_the_same_ffi_call_as_the_reference():
+    """Rows (f)1 / (f)3 host logic: for ~110 user-level expressions on vectors and matrices (eadd / emult / apply /
+    assign / extract / reduce / select / pattern / transpose, every arithmetic operator incl. the reflected and in-place
+    forms, operators from `with` contexts and strings, Scalar operands, masks, accumulators, descriptors, casts) the
+    mirror hands the C ABI the same function, operator handles, operands (in the same order), scalars, index lists and
+    descriptor as the unmodified reference does.  Nothing computes: both run on the recorder of tests/ffi_recorder.py."""
+    r = _run("""
+        import sys
+        sys.path.insert(0, %r)
+        from ffi_recorder import *
+        def _with(cm, fn):
+            with cm:
+                return fn()
+        exec(%r)
+        bad = []
+        for k, fn in cases.items():
+            a, b = both(fn)
+            if a != b:
+                bad.append((k, a, b))
+            elif a[:1] == ("EXC",) and k != "m_inv":
+                bad.append((k, "raises in both", a))
+        assert not bad, bad
+        print("OK", len(cases))
+    """ % (os.path.join(ROOT, "tests"), FFI_CASES))
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

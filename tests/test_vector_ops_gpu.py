@@ -204,13 +204,20 @@ def test_random_ewise_apply_assign(seed):
             gu.apply(getattr(util.g_type(optype), uop), out=gw, mask=gm, accum=gacc, desc=dg)
             Tm, zt = vm.apply(uop, optype, _dict(u))
         else:
-            s = int(rng.integers(-3, 4)) if seed % 2 else float(rng.integers(-6, 7)) / 2
-            st = "INT64" if isinstance(s, int) else "FP64"
+            # the bound scalar travels through the typed entry point of the VECTOR's type (vector.py:1293-1299, 1345-1351)
+            if ut == "BOOL":
+                s = bool(rng.integers(0, 2))
+            elif ut in ("FP32", "FP64"):
+                s = float(rng.integers(-6, 7)) / 2
+            elif ut.startswith("U"):
+                s = int(rng.integers(0, 4))
+            else:
+                s = int(rng.integers(-3, 4))
             if sub == 1:
                 gu.apply_first(s, gop, out=gw, mask=gm, accum=gacc, desc=dg)
             else:
                 gu.apply_second(gop, s, out=gw, mask=gm, accum=gacc, desc=dg)
-            Tm, zt = vm.bind(op, optype, s, st, _dict(u), first=(sub == 1))
+            Tm, zt = vm.bind(op, optype, DT[ut](s), ut, _dict(u), first=(sub == 1))
         exp = vm.write(_dict(w), wt, mm, accum, Tm, zt, dm)
     elif kind == 3:    # assign scalar / vector over GrB_ALL, a stride and an index list
         sub = seed % 3
