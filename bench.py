@@ -129,34 +129,45 @@ def cpu_spmv(n, indptr, indices, vals, u, min_seconds, max_reps):
     from oracle import oracle as orc
     L = orc.lib()
     L.fast_num_threads.restype = ctypes.c_int
+    L.fast_spmv_plan_f32.restype = ctypes.c_void_p
     w = np.zeros(n, np.float32)
     pres = np.zeros(n, np.uint8)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     args = (ctypes.c_int64(n), p(indptr), p(indices), p(vals), p(u), p(w), p(pres))
-    # all host cores, whatever OMP_NUM_THREADS says (torchrun exports 1); on SMT / multi-socket hosts fewer threads
-    # than logical CPUs are often faster for this gather-bound loop, so the thread count is chosen by measurement
-    # (best of three passes each at n, 3n/4, n/2 and n/4 threads) -- the baseline gets its best configuration
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun exports 1).  The baseline gets its best configuration,
+    # chosen by measurement (best of three passes each): n, 3n/4, n/2 and n/4 threads (on SMT / multi-socket hosts
+    # fewer threads than logical CPUs are often faster for this gather-bound loop) x two variants of the port --
+    # dynamic row chunks on the caller's arrays, or nnz-balanced per-thread partitions first-touched by their
+    # thread (NUMA placement) with prefetched gathers
     ncpu = len(os.sched_getaffinity(0))
     best = None
     for nt in sorted({ncpu, max(1, 3 * ncpu // 4), max(1, ncpu // 2), max(1, ncpu // 4)}, reverse=True):
         L.fast_set_threads(ctypes.c_int(nt))
-        L.fast_spmv_plus_times_f32(*args)      # warm-up / page-in
-        dt = None
-        for _ in range(3):
-            t0 = time.perf_counter()
-            L.fast_spmv_plus_times_f32(*args)
-            d = time.perf_counter() - t0
-            dt = d if dt is None or d < dt else dt
-        if best is None or dt < best[0]:
-            best = (dt, nt)
+        plan = ctypes.c_void_p(L.fast_spmv_plan_f32(ctypes.c_int64(n), p(indptr), p(indices), p(vals), ctypes.c_int(nt)))
+        for variant in ("rows", "plan"):
+            run = (lambda: L.fast_spmv_plus_times_f32(*args)) if variant == "rows" else (lambda: L.fast_spmv_plan_run_f32(plan, p(u), p(w), p(pres)))
+            run()                                  # warm-up / page-in
+            dt = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                run()
+                d = time.perf_counter() - t0
+                dt = d if dt is None or d < dt else dt
+            if best is None or dt < best[0]:
+                best = (dt, nt, variant)
+        L.fast_spmv_plan_free_f32(plan)
     L.fast_set_threads(ctypes.c_int(best[1]))
     cores = L.fast_num_threads()
+    plan = ctypes.c_void_p(L.fast_spmv_plan_f32(ctypes.c_int64(n), p(indptr), p(indices), p(vals), ctypes.c_int(best[1]))) if best[2] == "plan" else None
+    run = (lambda: L.fast_spmv_plan_run_f32(plan, p(u), p(w), p(pres))) if plan else (lambda: L.fast_spmv_plus_times_f32(*args))
     times = []
     t_all = time.perf_counter()
     while len(times) < max_reps and (time.perf_counter() - t_all < min_seconds or len(times) < 3):
         t0 = time.perf_counter()
-        L.fast_spmv_plus_times_f32(*args)
+        run()
         times.append(time.perf_counter() - t0)
+    if plan:
+        L.fast_spmv_plan_free_f32(plan)
     return cores, times, w, pres
 
 

@@ -113,6 +113,14 @@ def test_fast_kernels_match_oracle():
     wo = orc.mxv(orc.SpVec("FP32", n), None, None, ("PLUS", "TIMES", "FP32"), Ao, orc.SpVec("FP32", n, np.arange(n), u))
     assert np.array_equal(np.nonzero(pres)[0], wo.I)
     assert np.allclose(w[pres != 0], wo.X, rtol=1e-5)
+    # the partitioned / first-touch variant of the same kernel (bench.py reports the faster of the two)
+    L.fast_spmv_plan_f32.restype = ctypes.c_void_p
+    for nt in (1, 3, 8):
+        plan = ctypes.c_void_p(L.fast_spmv_plan_f32(ctypes.c_int64(n), p(indptr), p(indices), p(vals), ctypes.c_int(nt)))
+        w2 = np.full(n, -1, np.float32); pres2 = np.full(n, 9, np.uint8)
+        L.fast_spmv_plan_run_f32(plan, p(u), p(w2), p(pres2))
+        L.fast_spmv_plan_free_f32(plan)
+        assert np.array_equal(pres2, pres) and np.allclose(w2, w, rtol=1e-6, atol=0), nt
     # masked plus_pair (triangle kernel), both formulations
     Ls = sp.tril(sp.csr_matrix((np.ones(nnz), indices, indptr), shape=(n, n)) + sp.csr_matrix((np.ones(nnz), indices, indptr), shape=(n, n)).T, -1).tocsr()
     Ls.sort_indices()
