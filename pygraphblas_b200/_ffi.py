@@ -34,6 +34,8 @@ def header_cdef():
             continue
         if s.startswith("#") or s.startswith('extern "C"') or s == "}":
             continue
+        if s.startswith("extern const double "):   # ABI mode cannot read `const double` constants; as variables it can
+            line = line.replace("extern const double ", "extern double ")
         out.append(line)
     return "\n".join(out)
 

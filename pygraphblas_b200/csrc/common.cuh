@@ -85,8 +85,13 @@ struct Csr {
     bool valid = false;
 };
 
+// per-object storage hints of SuiteSparse's GxB_*_Option_set/get: recorded and reported back, without effect on the HBM
+// layout (always CSR by row / dense + presence) -- the API is format-agnostic, results do not depend on them
+struct GBObjOpts { double hyper = 0.0625; int format = 0 /* GxB_BY_ROW */; int sparsity = 15 /* GxB_AUTO_SPARSITY */; };
+
 struct GB_Matrix_opaque {
     int magic; GrB_Type type; uint64_t nrows, ncols;
+    GBObjOpts opts;
     // host form: row-major sorted unique COO
     std::vector<uint64_t> hi, hj; std::vector<uint8_t> hx; bool host_valid;
     // pending setElement tuples (in call order; later wins)
@@ -98,6 +103,7 @@ struct GB_Matrix_opaque {
 
 struct GB_Vector_opaque {
     int magic; GrB_Type type; uint64_t n;
+    GBObjOpts opts;
     // host form: sorted unique (index, value)
     std::vector<uint64_t> hi; std::vector<uint8_t> hx; bool host_valid;
     std::vector<uint64_t> pi; std::vector<uint8_t> px;

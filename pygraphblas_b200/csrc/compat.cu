@@ -139,7 +139,8 @@ extern "C" GrB_Info GxB_Global_Option_set(GxB_Option_Field field, ...) {
         case GxB_BURBLE: g_opt.burble = va_arg(ap, int); break;
         case GxB_HYPER_SWITCH: g_opt.hyper = va_arg(ap, double); break;
         case GxB_BITMAP_SWITCH: { const double *p = va_arg(ap, const double *); if (p) memcpy(g_opt.bitmap, p, sizeof g_opt.bitmap); } break;
-        case GxB_FORMAT: { const int f = va_arg(ap, int); if (f == GxB_BY_ROW) g_opt.format = f; else r = gb_fail(GrB_INVALID_VALUE, nullptr, "GxB_FORMAT: only GxB_BY_ROW (CSR) is supported"); } break;
+        case GxB_FORMAT: { const int f = va_arg(ap, int);                // default storage hint of new matrices: recorded, no effect on the HBM layout
+            if (f == GxB_BY_ROW || f == GxB_BY_COL) g_opt.format = f; else r = gb_fail(GrB_INVALID_VALUE, nullptr, "GxB_FORMAT: GxB_BY_ROW or GxB_BY_COL"); } break;
         default: r = gb_fail(GrB_INVALID_VALUE, nullptr, "GxB_Global_Option_set: unknown option %d", (int)field);
     }
     va_end(ap); return r;
@@ -160,41 +161,43 @@ extern "C" GrB_Info GxB_Global_Option_get(GxB_Option_Field field, ...) {
     }
     va_end(ap); return r;
 }
-static GrB_Info object_option_set(GxB_Option_Field field, va_list ap) {
+static GrB_Info object_option_set(GBObjOpts &o, GxB_Option_Field field, va_list ap) {
     switch (field) {
-        case GxB_HYPER_SWITCH: (void)va_arg(ap, double); return GrB_SUCCESS;
+        case GxB_HYPER_SWITCH: o.hyper = va_arg(ap, double); return GrB_SUCCESS;
         case GxB_BITMAP_SWITCH: (void)va_arg(ap, double); return GrB_SUCCESS;
-        case GxB_SPARSITY_CONTROL: (void)va_arg(ap, int); return GrB_SUCCESS;      // HBM layout is fixed (CSR / dense+presence)
-        case GxB_FORMAT: { const int f = va_arg(ap, int); return f == GxB_BY_ROW ? GrB_SUCCESS : gb_fail(GrB_INVALID_VALUE, nullptr, "GxB_FORMAT: only GxB_BY_ROW (CSR) is supported"); }
+        case GxB_SPARSITY_CONTROL: o.sparsity = va_arg(ap, int); return GrB_SUCCESS;      // HBM layout is fixed (CSR / dense+presence)
+        case GxB_FORMAT: { const int f = va_arg(ap, int);                                   // a storage hint: recorded, no effect
+            if (f != GxB_BY_ROW && f != GxB_BY_COL) return gb_fail(GrB_INVALID_VALUE, nullptr, "GxB_FORMAT: GxB_BY_ROW or GxB_BY_COL");
+            o.format = f; return GrB_SUCCESS; }
         default: return gb_fail(GrB_INVALID_VALUE, nullptr, "Option_set: unknown option %d", (int)field);
     }
 }
-static GrB_Info object_option_get(GxB_Option_Field field, bool huge, va_list ap) {
+static GrB_Info object_option_get(const GBObjOpts &o, GxB_Option_Field field, bool huge, va_list ap) {
     void *out = va_arg(ap, void *);
     if (!out) return gb_fail(GrB_NULL_POINTER, nullptr, "Option_get: NULL");
     switch (field) {
-        case GxB_HYPER_SWITCH: *(double *)out = g_opt.hyper; return GrB_SUCCESS;
+        case GxB_HYPER_SWITCH: *(double *)out = o.hyper; return GrB_SUCCESS;
         case GxB_BITMAP_SWITCH: *(double *)out = 0.04; return GrB_SUCCESS;
-        case GxB_FORMAT: *(int *)out = GxB_BY_ROW; return GrB_SUCCESS;
-        case GxB_SPARSITY_CONTROL: *(int *)out = GxB_AUTO_SPARSITY; return GrB_SUCCESS;
+        case GxB_FORMAT: *(int *)out = o.format; return GrB_SUCCESS;
+        case GxB_SPARSITY_CONTROL: *(int *)out = o.sparsity; return GrB_SUCCESS;
         case GxB_SPARSITY_STATUS: *(int *)out = huge ? GxB_HYPERSPARSE : GxB_SPARSE; return GrB_SUCCESS;
         default: return gb_fail(GrB_INVALID_VALUE, nullptr, "Option_get: unknown option %d", (int)field);
     }
 }
 extern "C" GrB_Info GxB_Matrix_Option_set(GrB_Matrix A, GxB_Option_Field field, ...) {
     if (!gb_valid_matrix(A)) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "GxB_Matrix_Option_set: invalid matrix");
-    va_list ap; va_start(ap, field); const GrB_Info r = object_option_set(field, ap); va_end(ap); return r;
+    va_list ap; va_start(ap, field); const GrB_Info r = object_option_set(A->opts, field, ap); va_end(ap); return r;
 }
 extern "C" GrB_Info GxB_Matrix_Option_get(GrB_Matrix A, GxB_Option_Field field, ...) {
     if (!gb_valid_matrix(A)) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "GxB_Matrix_Option_get: invalid matrix");
     // host-only tuple form (no HBM CSR yet, or dimensions beyond 2^31) reports HYPERSPARSE, tests/test_matrix.py:555,570
-    va_list ap; va_start(ap, field); const GrB_Info r = object_option_get(field, !A->dev.valid, ap); va_end(ap); return r;
+    va_list ap; va_start(ap, field); const GrB_Info r = object_option_get(A->opts, field, !A->dev.valid, ap); va_end(ap); return r;
 }
 extern "C" GrB_Info GxB_Vector_Option_set(GrB_Vector v, GxB_Option_Field field, ...) {
     if (!gb_valid_vector(v)) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "GxB_Vector_Option_set: invalid vector");
-    va_list ap; va_start(ap, field); const GrB_Info r = object_option_set(field, ap); va_end(ap); return r;
+    va_list ap; va_start(ap, field); const GrB_Info r = object_option_set(v->opts, field, ap); va_end(ap); return r;
 }
 extern "C" GrB_Info GxB_Vector_Option_get(GrB_Vector v, GxB_Option_Field field, ...) {
     if (!gb_valid_vector(v)) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "GxB_Vector_Option_get: invalid vector");
-    va_list ap; va_start(ap, field); const GrB_Info r = object_option_get(field, !v->dev_valid, ap); va_end(ap); return r;
+    va_list ap; va_start(ap, field); const GrB_Info r = object_option_get(v->opts, field, !v->dev_valid, ap); va_end(ap); return r;
 }
