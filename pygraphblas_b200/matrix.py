@@ -105,6 +105,30 @@ class Matrix:
         return cls.from_lists(I, J, V, nrows, ncols, typ)
 
     @classmethod
+    def identity(cls, typ, nrows, value=None):
+        """Square matrix with `value` (default one) on the diagonal (matrix.py:574-594 of the reference), built in bulk."""
+        d = np.arange(nrows, dtype=np.uint64)
+        return cls.from_lists(d, d, np.full(nrows, 1 if value is None else value, dtype=typ.dtype), nrows, nrows, typ)
+
+    @classmethod
+    def from_scipy_sparse(cls, m):
+        """Type inferred from m.dtype (matrix.py:3495-3514); goes through the host tuple form like the reference
+        (`from_scipy` is the bulk route straight into HBM)."""
+        ss = m.tocoo()
+        return cls.from_lists(ss.row, ss.col, ss.data, ss.shape[0], ss.shape[1], types._dtype_lookup(m.dtype))
+
+    def to_scipy_sparse(self, format="csr"):
+        """(matrix.py:3516-3534)"""
+        from scipy import sparse
+        rows, cols, vals = self.to_arrays()
+        s = sparse.coo_matrix((vals, (rows.astype(np.int64), cols.astype(np.int64))), shape=self.shape, dtype=self.type.dtype)
+        if format == "coo":
+            return s
+        if format not in {"bsr", "csr", "csc", "coo", "lil", "dia", "dok"}:
+            raise TypeError(f"Invalid format: {format}")
+        return s.asformat(format)
+
+    @classmethod
     def from_scipy(cls, A, typ=None):
         A = A.tocsr()
         A.sort_indices()

@@ -48,6 +48,11 @@ class Vector:
         return v
 
     @classmethod
+    def from_1_to_n(cls, n):
+        """(vector.py:370-382)"""
+        return cls.from_lists(np.arange(n, dtype=np.uint64), np.arange(1, n + 1, dtype=np.int64), n, types.INT64)
+
+    @classmethod
     def from_list(cls, V, typ=None):
         return cls.from_lists(list(range(len(V))), V, len(V), typ)
 

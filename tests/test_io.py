@@ -62,3 +62,16 @@ def test_tsv_read_known_answer(tmp_path):
     f.write_text("1\t1\t2\n2\t2\t3\n3\t3\t4\n")
     n = Matrix.from_tsv(f, INT8, 3, 3)
     assert n.type is INT8 and n.to_lists() == [[0, 1, 2], [0, 1, 2], [2, 3, 4]]
+
+
+def test_convenience_constructors_known_answers():
+    """matrix.py:574-594 (identity doctest), vector.py:370-382 (from_1_to_n), tests/test_matrix.py:1060-1068 (scipy round trip)"""
+    import scipy.sparse as sp
+    from pygraphblas_b200 import Vector, UINT8
+    assert Matrix.identity(UINT8, 3, 42).to_lists() == [[0, 1, 2], [0, 1, 2], [42, 42, 42]]
+    assert Matrix.identity(FP64, 2).to_lists() == [[0, 1], [0, 1], [1.0, 1.0]]
+    assert Vector.from_1_to_n(3).to_lists() == [[0, 1, 2], [1, 2, 3]]
+    m = Matrix.from_lists([0, 1, 2], [1, 2, 0], [1, 2, 3])
+    s = m.to_scipy_sparse()
+    assert sp.isspmatrix_csr(s) and s.dtype == np.int64 and (s.toarray() == np.array([[0, 1, 0], [0, 0, 2], [3, 0, 0]])).all()
+    assert Matrix.from_scipy_sparse(s).iseq(m) and m.to_scipy_sparse("coo").nnz == 3
