@@ -221,6 +221,12 @@ uint64_t B200_kernel_launches(void);
 /* per-matrix SpGEMM/SpMV work figures of the most recent GrB_mxm (flops = number of
  * multiplies, nnz_out = nvals of the semiring product before accum/mask) */
 GrB_Info B200_last_mxm_stats(uint64_t *flops, uint64_t *nnz_out);
+/* kernel-choice switches (B200GRB_* environment variables) are read once at GrB_init; re-read them now */
+GrB_Info B200_reload_tunables(void);
+/* same switch as GxB_Global_Option_set(GxB_BURBLE, on) (/root/reference/pygraphblas/base.py:84-86): every compute
+ * call prints the kernel it chose, its algorithmic bytes and its device time */
+void B200_set_burble(int on);
+int B200_get_burble(void);
 
 /* ------------------------------------------------------------------ import compatibility
  * Names the unmodified reference package resolves at import time or calls around its hot-path tests

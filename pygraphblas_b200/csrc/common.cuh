@@ -77,11 +77,16 @@ struct Csr {
     uint32_t *nzrow = nullptr;       // [nnzrows] ids of the non-empty rows, ascending
     uint8_t *pres_tmpl = nullptr;    // [nrows] 1 where the row is non-empty
     int64_t nruns = 0, nnzrows = 0;
-    // hot-column plan (spmv.cu): columns relabelled by descending in-degree
-    uint32_t *hperm = nullptr;     // [ncols] new id -> original column
-    uint32_t *hcol = nullptr;      // [nnz] relabelled column ids
-    int64_t hused = 0;             // columns that occur at least once
-    double hot_cover = 0.0;        // share of the entries whose column is among the 40960 most referenced
+    // hot-column plan (spmv_run.cu): the henc most referenced columns get their rank as id, the others col + henc
+    uint32_t *hperm = nullptr;     // [henc] hot rank -> original column
+    uint32_t *hcol = nullptr;      // [nnz] encoded column ids
+    uint32_t henc = 0;             // ids below this are hot ranks
+    bool hot_planned = false;      // the plan was attempted (hcol stays NULL when the gathers are not concentrated)
+    double hot_cover = 0.0;        // share of the entries whose column is among the henc most referenced
+    // per-call scratch of the run kernels, kept with the plan (no allocation on the call path)
+    void *ws_head = nullptr, *ws_tail = nullptr;   // [nruns] x 8 bytes: partials of the rows a run starts / ends inside
+    uint8_t *ws_head_has = nullptr, *ws_tail_has = nullptr;
+    void *ws_uhot = nullptr;       // [henc] x 8 bytes: u at the hot columns
     bool valid = false;
 };
 
@@ -121,6 +126,8 @@ struct GBGlobal {
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
     uint64_t last_flops = 0, last_nnz_out = 0;
+    int burble = 0;
+    cudaEvent_t burble_e0 = nullptr, burble_e1 = nullptr;
     std::recursive_mutex mu;
 };
 extern GBGlobal G;
@@ -141,6 +148,26 @@ static inline void gb_thread_enter() {
     return gb_fail(_e == cudaErrorMemoryAllocation ? GrB_OUT_OF_MEMORY : GrB_PANIC, errstr, \
                    "CUDA error %s at %s:%d", cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
 
+// kernel-choice switches read from the environment ONCE (GrB_init) and again only on B200_reload_tunables()
+// (tests flip them between calls); nothing on a call path touches getenv
+struct Tunables {
+    int spmv_items = 8;        // B200GRB_SPMV_ITEMS   entries per thread of the tile kernel (4 / 8 / 16)
+    int spmv_run = -1;         // B200GRB_SPMV_RUN     -1 default choice, 0 never, 1 always the run kernel
+    int spmv_hot_kb = -1;      // B200GRB_SPMV_HOT     -1 default (on when the gathers are concentrated), 0 off, >0 table cap in KB
+    bool no_pull = false, no_push = false, force_push = false, spmv_debug = false;
+    int spgemm_v = 0;          // B200GRB_SPGEMM_V     masked SpGEMM kernel generation (0 = default)
+};
+const Tunables &tunables();
+
+// GxB_BURBLE (/root/reference/pygraphblas/base.py:84-86): when on, every compute entry point prints which kernel it
+// chose, the algorithmic bytes of the call and its device time; every entry point is also an NVTX range
+struct GbBurble {
+    bool on; const char *fn; const char *kernel = ""; double bytes = 0.0;
+    explicit GbBurble(const char *fn);
+    void note(const char *k, double b) { kernel = k; bytes = b; }
+    ~GbBurble();
+};
+
 // device memory (stream-ordered pool on G.stream)
 GrB_Info dmalloc(void **p, size_t bytes, std::string *err);
 void dfree(void *p);
@@ -148,6 +175,7 @@ template <typename T> static inline GrB_Info dalloc(T **p, size_t count, std::st
     return dmalloc((void **)p, count * sizeof(T) + 16, err);   // +16: bulk copies may over-read a tail
 }
 void csr_free(Csr &c);
+void csr_drop_plans(Csr &c);
 
 // host <-> device sync of containers (objects.cu)
 GrB_Info matrix_flush_pending(GrB_Matrix A);

@@ -136,7 +136,7 @@ extern "C" GrB_Info GxB_Global_Option_set(GxB_Option_Field field, ...) {
     switch (field) {
         case GxB_GLOBAL_NTHREADS: g_opt.nthreads = va_arg(ap, int); break;
         case GxB_GLOBAL_CHUNK: g_opt.chunk = va_arg(ap, double); break;
-        case GxB_BURBLE: g_opt.burble = va_arg(ap, int); break;
+        case GxB_BURBLE: g_opt.burble = va_arg(ap, int); G.burble = g_opt.burble; break;
         case GxB_HYPER_SWITCH: g_opt.hyper = va_arg(ap, double); break;
         case GxB_BITMAP_SWITCH: { const double *p = va_arg(ap, const double *); if (p) memcpy(g_opt.bitmap, p, sizeof g_opt.bitmap); } break;
         case GxB_FORMAT: { const int f = va_arg(ap, int);                // default storage hint of new matrices: recorded, no effect on the HBM layout
@@ -152,7 +152,7 @@ extern "C" GrB_Info GxB_Global_Option_get(GxB_Option_Field field, ...) {
     else switch (field) {
         case GxB_GLOBAL_NTHREADS: *(int *)out = g_opt.nthreads; break;
         case GxB_GLOBAL_CHUNK: *(double *)out = g_opt.chunk; break;
-        case GxB_BURBLE: *(int *)out = g_opt.burble; break;
+        case GxB_BURBLE: *(int *)out = G.burble; break;
         case GxB_HYPER_SWITCH: *(double *)out = g_opt.hyper; break;
         case GxB_BITMAP_SWITCH: memcpy(out, g_opt.bitmap, sizeof g_opt.bitmap); break;
         case GxB_FORMAT: *(int *)out = g_opt.format; break;

@@ -82,10 +82,7 @@ __global__ void narrow_rowptr_kernel(const int64_t *rp, uint32_t *rp32, int64_t 
 }
 GrB_Info dev_build_rowptr32(Csr &c, std::string *err) {
     dfree(c.rowptr32); c.rowptr32 = nullptr;
-    dfree(c.tile_row); c.tile_row = nullptr; c.ntiles = 0; c.tile_size = 0;
-    dfree(c.hperm); dfree(c.hcol); c.hperm = nullptr; c.hcol = nullptr; c.hused = 0;
-    dfree(c.run_headw); dfree(c.run_lane); dfree(c.run_base); dfree(c.run_tail_row); dfree(c.run_tail_last); dfree(c.nzrow); dfree(c.pres_tmpl);
-    c.run_headw = nullptr; c.run_lane = nullptr; c.run_base = nullptr; c.run_tail_row = nullptr; c.run_tail_last = nullptr; c.nzrow = nullptr; c.pres_tmpl = nullptr; c.nruns = 0; c.nnzrows = 0;
+    csr_drop_plans(c);
     if (c.nnz >= ((int64_t)1 << 32)) return GrB_SUCCESS;
     GB_TRY(dalloc(&c.rowptr32, (size_t)c.nrows + 1, err));
     const int64_t n = c.nrows + 1;

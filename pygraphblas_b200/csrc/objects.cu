@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <numeric>
 #include <unordered_map>
+#include <nvtx3/nvToolsExt.h>
 
 GBGlobal G;
 thread_local std::string tl_error;
@@ -30,6 +31,45 @@ GrB_Info gb_fail(GrB_Info code, std::string *where, const char *fmt, ...) {
 }
 
 extern "C" const char *B200_last_error(void) { return tl_error.c_str(); }
+
+// ------------------------------------------------------------------ tunables, burble, NVTX
+static Tunables g_tun; static bool g_tun_loaded = false;
+static void tunables_load() {
+    Tunables t;
+    auto geti = [](const char *k, int d) { const char *e = getenv(k); return e ? atoi(e) : d; };
+    t.spmv_items = geti("B200GRB_SPMV_ITEMS", 8);
+    t.spmv_run = geti("B200GRB_SPMV_RUN", -1);
+    t.spmv_hot_kb = geti("B200GRB_SPMV_HOT", -1);
+    t.no_pull = getenv("B200GRB_NO_PULL") != nullptr; t.no_push = getenv("B200GRB_NO_PUSH") != nullptr;
+    t.force_push = getenv("B200GRB_FORCE_PUSH") != nullptr; t.spmv_debug = getenv("B200GRB_SPMV_DEBUG") != nullptr;
+    t.spgemm_v = geti("B200GRB_SPGEMM_V", 0);
+    g_tun = t; g_tun_loaded = true;
+}
+const Tunables &tunables() { if (!g_tun_loaded) tunables_load(); return g_tun; }
+extern "C" GrB_Info B200_reload_tunables(void) { GB_LOCK; tunables_load(); return GrB_SUCCESS; }
+
+GbBurble::GbBurble(const char *f) : on(G.burble != 0 && G.have_device), fn(f) {
+    nvtxRangePushA(f);
+    if (on) {
+        if (!G.burble_e0) { cudaEventCreate(&G.burble_e0); cudaEventCreate(&G.burble_e1); }
+        cudaEventRecord(G.burble_e0, G.stream);
+    }
+}
+GbBurble::~GbBurble() {
+    if (on) {
+        cudaEventRecord(G.burble_e1, G.stream);
+        float ms = 0.f;
+        if (cudaEventSynchronize(G.burble_e1) == cudaSuccess && cudaEventElapsedTime(&ms, G.burble_e0, G.burble_e1) == cudaSuccess) {
+            const double us = ms * 1e3;
+            printf(" [ B200 %s: kernel %s, %.3f MB algorithmic, %.1f us on the device", fn, kernel, bytes / 1e6, us);
+            if (us > 0 && bytes > 0) printf(", %.1f GB/s", bytes / (us * 1e-6) / 1e9);
+            printf(" ]\n"); fflush(stdout);
+        }
+    }
+    nvtxRangePop();
+}
+extern "C" void B200_set_burble(int on) { G.burble = on; }
+extern "C" int B200_get_burble(void) { return G.burble; }
 
 // ------------------------------------------------------------------ types
 static GB_Type_opaque type_BOOL   = {GB_MAGIC, TC_BOOL, 1, "BOOL"};
@@ -99,6 +139,7 @@ extern "C" GrB_Info GrB_init(GrB_Mode mode) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     G.have_device = true;
+    tunables_load();
     return GrB_SUCCESS;
 }
 
@@ -129,8 +170,19 @@ GrB_Info dmalloc(void **p, size_t bytes, std::string *err) {
 }
 void dfree(void *p) { if (p && G.have_device) cudaFreeAsync(p, G.stream); }
 
+// the cached SpMV plans and scratch of a CSR (dropped whenever its structure changes)
+void csr_drop_plans(Csr &c) {
+    dfree(c.tile_row); c.tile_row = nullptr; c.ntiles = 0; c.tile_size = 0;
+    dfree(c.hperm); dfree(c.hcol); c.hperm = nullptr; c.hcol = nullptr; c.henc = 0; c.hot_planned = false; c.hot_cover = 0.0;
+    dfree(c.run_headw); dfree(c.run_lane); dfree(c.run_base); dfree(c.run_tail_row); dfree(c.run_tail_last); dfree(c.nzrow); dfree(c.pres_tmpl);
+    c.run_headw = nullptr; c.run_lane = nullptr; c.run_base = nullptr; c.run_tail_row = nullptr; c.run_tail_last = nullptr; c.nzrow = nullptr; c.pres_tmpl = nullptr;
+    c.nruns = 0; c.nnzrows = 0;
+    dfree(c.ws_head); dfree(c.ws_tail); dfree(c.ws_head_has); dfree(c.ws_tail_has); dfree(c.ws_uhot);
+    c.ws_head = c.ws_tail = c.ws_uhot = nullptr; c.ws_head_has = c.ws_tail_has = nullptr;
+}
 void csr_free(Csr &c) {
-    dfree(c.rowptr); dfree(c.rowptr32); dfree(c.col); dfree(c.val); dfree(c.tile_row); dfree(c.hperm); dfree(c.hcol); dfree(c.run_headw); dfree(c.run_lane); dfree(c.run_base); dfree(c.run_tail_row); dfree(c.run_tail_last); dfree(c.nzrow); dfree(c.pres_tmpl);
+    csr_drop_plans(c);
+    dfree(c.rowptr); dfree(c.rowptr32); dfree(c.col); dfree(c.val);
     c = Csr();
 }
 

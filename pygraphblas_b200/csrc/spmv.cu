@@ -84,10 +84,9 @@ static GrB_Info spmv_plan(Csr &c, int tile, std::string *err) {
 // SPARSE: u has a presence array (entries with absent u(k) do not contribute).
 // Everything after the column / value words of a tile are in registers: gather u, mark rows, fold,
 // scan, write.  `sync` is the barrier of the 256 threads that share s_head / s_wv / s_wflag.
-template <typename XT, typename ZT, int ADD, int MUL, bool SPARSE, int IT, bool HOT, typename Sync>
+template <typename XT, typename ZT, int ADD, int MUL, bool SPARSE, int IT, typename Sync>
 __device__ __forceinline__ void spmv_tile_finish(const SpmvArgs &p, const uint32_t tile, const int tid, const int tlen, const int nvalid,
-                                                 uint32_t (&c)[IT], XT (&a)[IT], int32_t *s_head, ZT *s_wv, int *s_wflag,
-                                                 const XT *s_hot, const uint32_t hot_n, Sync &&sync) {
+                                                 uint32_t (&c)[IT], XT (&a)[IT], int32_t *s_head, ZT *s_wv, int *s_wflag, Sync &&sync) {
     constexpr int TILE = SPMV_THREADS * IT;
     constexpr bool NEED_A = MUL < 0 || mul_reads_x(MUL);
     constexpr bool NEED_U = MUL < 0 || mul_reads_y(MUL);
@@ -116,8 +115,7 @@ __device__ __forceinline__ void spmv_tile_finish(const SpmvArgs &p, const uint32
     if (NEED_U) {
 #pragma unroll
         for (int j = 0; j < IT; ++j) {
-            if (HOT && c[j] < hot_n) uv[j] = s_hot[c[j]];                     // hot column: shared-memory table, no L1 wavefront
-            else uv[j] = gload<XT>(uval + c[j]);
+            uv[j] = gload<XT>(uval + c[j]);
         }
     }
     sync();                                                               // head marks are clear
@@ -246,58 +244,8 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_tile_kernel(const SpmvArgs 
             if (NEED_A) a[j] = j < nvalid ? avalp[j] : (XT)1;
         }
     }
-    spmv_tile_finish<XT, ZT, ADD, MUL, SPARSE, IT, false>(p, tile, tid, tlen, nvalid, c, a, s_head, s_wv, s_wflag, nullptr, 0u, [] { __syncthreads(); });
+    spmv_tile_finish<XT, ZT, ADD, MUL, SPARSE, IT>(p, tile, tid, tlen, nvalid, c, a, s_head, s_wv, s_wflag, [] { __syncthreads(); });
 }
-
-// Hot-column variant (dense u, specialised semirings, large matrices).  A scattered 4-byte gather
-// costs one L1 wavefront per lane, which bounds the general kernel near nnz / (SMs x clock); gathers
-// served from shared memory cost a few bank-conflict cycles per warp instead.  The matrix's columns are
-// relabelled once by descending in-degree (cached plan), so the hot_n most referenced entries of the
-// permuted u form a dense table; persistent CTAs of GROUPS x 256 threads load it once and stride over
-// the tiles (on R-MAT graphs the top 32 K of 4 M columns take 53 % of all gathers).
-template <typename ZT> __host__ __device__ constexpr size_t hot_group_bytes() { return SPMV_THREADS * 8 * 4 + SPMV_WARPS * 16; }
-template <typename XT, typename ZT, int ADD, int MUL, int GROUPS>
-__global__ void __launch_bounds__(SPMV_THREADS * GROUPS, (GROUPS == 4 ? 1 : (GROUPS == 3 ? 2 : (GROUPS == 2 ? 3 : 6)))) spmv_hot_kernel(const SpmvArgs p, const uint32_t hot_n) {
-    constexpr int IT = 8;
-    constexpr int TILE = SPMV_THREADS * IT;
-    constexpr bool NEED_A = mul_reads_x(MUL);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int group = threadIdx.x / SPMV_THREADS, tid = threadIdx.x % SPMV_THREADS;
-    unsigned char *gbase = smem_raw + (size_t)group * hot_group_bytes<ZT>();
-    int32_t *s_head = reinterpret_cast<int32_t *>(gbase);
-    ZT *s_wv = reinterpret_cast<ZT *>(gbase + TILE * 4);
-    int *s_wflag = reinterpret_cast<int *>(gbase + TILE * 4 + SPMV_WARPS * 8);
-    XT *s_hot = reinterpret_cast<XT *>(smem_raw + GROUPS * hot_group_bytes<ZT>());
-    const XT *uval = static_cast<const XT *>(p.uval);
-    for (uint32_t i = threadIdx.x; i < hot_n; i += blockDim.x) s_hot[i] = uval[i];
-    __syncthreads();
-    auto sync = [group] { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(SPMV_THREADS) : "memory"); };
-    for (int64_t tile = (int64_t)blockIdx.x * GROUPS + group; tile < p.ntiles; tile += (int64_t)gridDim.x * GROUPS) {
-        const int64_t tstart = tile * TILE;
-        const int tlen = (int)min((int64_t)TILE, p.nnz - tstart);
-        const int loc0 = tid * IT;
-        const int nvalid = min(max(tlen - loc0, 0), IT);
-        const uint32_t *colp = p.col + tstart + loc0;
-        const XT *avalp = static_cast<const XT *>(p.aval) + tstart + loc0;
-        uint32_t c[IT]; XT a[IT];
-        if (nvalid == IT) {
-#pragma unroll
-            for (int g = 0; g < IT / 4; ++g) {
-                load4<uint32_t>(colp + g * 4, &c[g * 4]);
-                if (NEED_A) load4<XT>(avalp + g * 4, &a[g * 4]);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < IT; ++j) {
-                c[j] = j < nvalid ? colp[j] : 0u;
-                if (NEED_A) a[j] = j < nvalid ? avalp[j] : (XT)1;
-            }
-        }
-        spmv_tile_finish<XT, ZT, ADD, MUL, false, IT, true>(p, (uint32_t)tile, tid, tlen, nvalid, c, a, s_head, s_wv, s_wflag, s_hot, hot_n, sync);
-        sync();                                                               // the group's shared memory is reused by its next tile
-    }
-}
-
 
 // ---- fix-up: rows that straddle tiles = tail partial of the tile they start in
 //      (+) head partials of the following tiles, combined by one warp in a fixed order
@@ -331,39 +279,8 @@ __global__ void clear_presence_kernel(uint8_t *p, int64_t n) {
 
 static int g_items_fast = 8, g_items_generic = 8;     // entries per thread (tunable: B200GRB_SPMV_ITEMS)
 
-struct HotLaunch { bool on; int64_t hused; int groups; size_t table_bytes; };
-static HotLaunch g_hot{false, 0, 4, (size_t)128 << 10};
-
-template <typename XT, typename ZT, int ADD, int MUL, int GROUPS>
-static void spmv_hot_launch(const SpmvArgs &a, const HotLaunch &h) {
-    auto kernel = spmv_hot_kernel<XT, ZT, ADD, MUL, GROUPS>;
-    int max_optin = 0;
-    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, G.device);
-    const size_t fixed = GROUPS * hot_group_bytes<ZT>();
-    size_t avail = (size_t)max_optin > fixed + 1024 ? (size_t)max_optin - fixed - 1024 : 0;
-    avail = std::min(avail, h.table_bytes);
-    const uint32_t hot_n = (uint32_t)std::min<int64_t>(h.hused, (int64_t)(avail / sizeof(XT)));
-    const size_t smem = fixed + (size_t)hot_n * sizeof(XT);
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SPMV_THREADS * GROUPS, smem);
-    per_sm = std::max(per_sm, 1);
-    const int ctas = (int)std::min<int64_t>((int64_t)G.num_sms * per_sm, ceil_div(a.ntiles, GROUPS));
-    kernel<<<ctas, SPMV_THREADS * GROUPS, smem, G.stream>>>(a, hot_n); GB_LAUNCHED();
-}
-
 template <typename XT, typename ZT, int ADD, int MUL, bool SPARSE, int IT>
 static void spmv_launch(const SpmvArgs &a) {
-    if constexpr (ADD >= 0 && !SPARSE && IT == 8) {
-        if (g_hot.on) {
-            if (g_hot.groups == 1) spmv_hot_launch<XT, ZT, ADD, MUL, 1>(a, g_hot);
-            else if (g_hot.groups == 2) spmv_hot_launch<XT, ZT, ADD, MUL, 2>(a, g_hot);
-            else if (g_hot.groups == 3) spmv_hot_launch<XT, ZT, ADD, MUL, 3>(a, g_hot);
-            else spmv_hot_launch<XT, ZT, ADD, MUL, 4>(a, g_hot);
-            spmv_fixup_kernel<ZT, ADD><<<(unsigned)ceil_div(a.ntiles * 32, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED();
-            return;
-        }
-    }
     spmv_tile_kernel<XT, ZT, ADD, MUL, SPARSE, IT><<<(unsigned)a.ntiles, SPMV_THREADS, 0, G.stream>>>(a); GB_LAUNCHED();
     spmv_fixup_kernel<ZT, ADD><<<(unsigned)ceil_div(a.ntiles * 32, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED();
 }
@@ -480,7 +397,9 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
     const bool sparse_u = u->dpres != nullptr;
     const bool fast_sr = !kflip && spmv_is_fast(xt, zt, add, kmul, false);      // a compile-time specialised semiring
     const bool fast = fast_sr && !sparse_u;
-    { const char *e = getenv("B200GRB_SPMV_ITEMS"); const int v = e ? atoi(e) : 8; g_items_fast = (v == 16 || v == 4) ? v : 8; }
+    const Tunables &tn = tunables();
+    GbBurble burble(fn);
+    g_items_fast = (tn.spmv_items == 16 || tn.spmv_items == 4) ? tn.spmv_items : 8;
     const int tile = SPMV_THREADS * (fast ? g_items_fast : g_items_generic);
     GB_TRY(spmv_plan(c, tile, err));
 
@@ -499,7 +418,7 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
     GB_TRY(dmalloc((void **)&tpres, (size_t)n + 16, err));
 
     // mask + saturating monoid (BFS-shaped): skip masked-out rows, stop rows at the first hit
-    const bool use_pull = mask != nullptr && (add == OP_LOR || add == OP_LAND || add == OP_ANY) && c.nnz > 0 && getenv("B200GRB_NO_PULL") == nullptr;
+    const bool use_pull = mask != nullptr && (add == OP_LOR || add == OP_LAND || add == OP_ANY) && c.nnz > 0 && !tn.no_pull;
     if (use_pull) {
         // the run-time-operator kernel reads both operands: make sure both are of the operand type
         if (aval == c.val && A->type->code != xt) { GB_TRY(dev_cast_values(&a_cast, xt, c.val, A->type->code, c.nnz, err)); aval = a_cast; }
@@ -507,7 +426,7 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
         // few frontier edges: push along the rows of the other orientation (already in HBM) instead of pulling every row
         bool pushed = false;
         const Csr &o = use_transpose ? A->dev : A->devT;
-        if (sparse_u && o.valid && o.rowptr32 && o.nnz == c.nnz && A->type->code == xt && getenv("B200GRB_NO_PUSH") == nullptr) {
+        if (sparse_u && o.valid && o.rowptr32 && o.nnz == c.nnz && A->type->code == xt && !tn.no_push) {
             PushArgs ps{};
             ps.rowptr = o.rowptr32; ps.col = o.col; ps.aval = o.val; ps.nin = o.nrows; ps.uval = uval; ps.upres = u->dpres;
             ps.mval = mask->dval; ps.mpres = mask->dpres; ps.mtc = mask->type->code; ps.mask_comp = f.mask_comp; ps.mask_struct = f.mask_struct;
@@ -530,47 +449,45 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
     // dense u + specialised semiring: warp-independent run kernel on the cached run plan
     const bool run_ok = !use_pull && (fast_sr || xt == zt || zt == TC_BOOL);     // specialised or run-time operators; dense or sparse u
     bool use_run = run_ok && c.nnz >= 4096;
-    if (const char *e = getenv("B200GRB_SPMV_RUN")) use_run = run_ok && c.nnz > 0 && atoi(e) != 0;
+    if (tn.spmv_run >= 0) use_run = run_ok && c.nnz > 0 && tn.spmv_run != 0;
+    const char *kernel_name = "pull";
     if (use_pull) {
         // done above
     } else if (use_run) {
         GB_TRY(spmv_run_plan(c, err));
-        CU_TRY(cudaMemsetAsync(tval, 0, (size_t)n * zsz, G.stream), err);
-        if (sparse_u) CU_TRY(cudaMemsetAsync(tpres, 0, (size_t)n, G.stream), err);     // presence follows u: written row by row
-        else CU_TRY(cudaMemcpyAsync(tpres, c.pres_tmpl, (size_t)n, cudaMemcpyDeviceToDevice, G.stream), err);
         RunArgs ra{};
         ra.col = c.col; ra.aval = aval; ra.uval = uval; ra.headw = c.run_headw; ra.lane_rank = c.run_lane; ra.run_base = c.run_base;
         ra.nzrow = c.nzrow; ra.rowptr = c.rowptr32; ra.nruns = c.nruns; ra.nnz = c.nnz; ra.tval = tval;
         ra.tail_row = c.run_tail_row; ra.tail_last = c.run_tail_last;
         ra.add_op = add; ra.mul_op = kmul; ra.flip = kflip;
-        GB_TRY(dmalloc(&ra.head_val, (size_t)c.nruns * zsz + 16, err));
-        GB_TRY(dmalloc(&ra.tail_val, (size_t)c.nruns * zsz + 16, err));
-        if (sparse_u) {
-            ra.upres = u->dpres; ra.tpres = tpres;
-            GB_TRY(dmalloc((void **)&ra.head_has, (size_t)c.nruns + 16, err));
-            GB_TRY(dmalloc((void **)&ra.tail_has, (size_t)c.nruns + 16, err));
-        }
-        void *u_perm = nullptr; size_t hot_bytes = 0;
+        ra.head_val = c.ws_head; ra.tail_val = c.ws_tail;            // scratch kept with the plan (the library serialises calls)
+        if (sparse_u) { ra.upres = u->dpres; ra.tpres = tpres; ra.head_has = c.ws_head_has; ra.tail_has = c.ws_tail_has; }
         // hot-column table: on by default for large matrices whose gathers are concentrated (R-MAT-like);
-        // B200GRB_SPMV_HOT=0 disables it, =<KB> forces a table size
-        const char *hot_env = getenv("B200GRB_SPMV_HOT");
-        int hot_kb = hot_env ? atoi(hot_env) : 160;
+        // B200GRB_SPMV_HOT=0 disables it, =<KB> caps the table size (and forces the kernel whatever the coverage)
+        int hot_kb = tn.spmv_hot_kb >= 0 ? tn.spmv_hot_kb : 224;
         if (fast && need_u && hot_kb > 0 && c.nnz >= ((int64_t)1 << 20) && c.ncols >= (1 << 16)) {
             GB_TRY(spmv_hot_plan(c, err));
-            if (!hot_env && c.hot_cover < 0.25) hot_kb = 0;
+            if (!c.hcol || (tn.spmv_hot_kb < 0 && c.hot_cover < 0.25)) hot_kb = 0;
         } else hot_kb = 0;
+        Hot2Args hot{};
         if (hot_kb > 0) {
-            const size_t xsz = (size_t)tc_size(xt);
-            GB_TRY(dmalloc(&u_perm, (size_t)c.hused * xsz + 16, err));
-            if (c.hused > 0) { spmv_permute_u(c.hperm, uval, u_perm, (int)xsz, c.hused); }
-            ra.col = c.hcol; ra.uval = u_perm; hot_bytes = (size_t)hot_kb << 10;
+            // one launch: u at the hot columns, T cleared, T's presence from the plan
+            spmv_hot2_prep(c, uval, tc_size(xt), tval, (size_t)n * zsz, tpres);
+            ra.col = c.hcol; hot.u_hot = c.ws_uhot; hot.henc = c.henc; hot.tab_n = 0;
+            kernel_name = "run+hot-table (TMA-staged)";
+        } else {
+            CU_TRY(cudaMemsetAsync(tval, 0, (size_t)n * zsz, G.stream), err);
+            if (sparse_u) CU_TRY(cudaMemsetAsync(tpres, 0, (size_t)n, G.stream), err);     // presence follows u: written row by row
+            else CU_TRY(cudaMemcpyAsync(tpres, c.pres_tmpl, (size_t)n, cudaMemcpyDeviceToDevice, G.stream), err);
+            kernel_name = sparse_u ? "run (sparse u)" : "run";
         }
-        const bool ok = fast_sr ? spmv_run_dispatch(xt, add, kmul, ra, hot_bytes, c.hused) : spmv_run_generic(xt, zt, ra);
-        dfree(u_perm); dfree(ra.head_val); dfree(ra.tail_val); dfree(ra.head_has); dfree(ra.tail_has);
+        const bool ok = fast_sr ? spmv_run_dispatch(xt, add, kmul, ra, hot_kb > 0 ? &hot : nullptr, (size_t)hot_kb << 10) : spmv_run_generic(xt, zt, ra);
         if (!ok) { dfree(tval); dfree(tpres); dfree(a_cast); dfree(u_cast); return gb_fail(GrB_PANIC, err, "mxv: internal dispatch error"); }
     } else if (c.nnz == 0) {
         clear_presence_kernel<<<grid_for(n), 256, 0, G.stream>>>(tpres, n); GB_LAUNCHED();
+        kernel_name = "empty";
     } else {
+        kernel_name = "tile";
         SpmvArgs a{};
         a.rowptr = c.rowptr32; a.col = c.col; a.aval = aval; a.tile_row = c.tile_row; a.ntiles = c.ntiles;
         a.nrows = c.nrows; a.nnz = c.nnz; a.uval = uval; a.upres = u->dpres; a.tval = tval; a.tpres = tpres;
@@ -580,20 +497,7 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
         GB_TRY(dmalloc((void **)&a.head_has, (size_t)c.ntiles + 16, err));
         GB_TRY(dmalloc((void **)&a.tail_has, (size_t)c.ntiles + 16, err));
         GB_TRY(dalloc(&a.tail_row, (size_t)c.ntiles, err));
-        // dense u on a large matrix with a specialised semiring: hot-column plan + shared-memory table
-        void *u_perm = nullptr;
-        g_hot.on = false;
-        const char *hot_env = getenv("B200GRB_SPMV_HOT");
-        if (fast && need_u && tile == SPMV_THREADS * 8 && c.nnz >= ((int64_t)1 << 20) && c.ncols >= (1 << 16) && hot_env && atoi(hot_env) > 0) {
-            GB_TRY(spmv_hot_plan(c, err));
-            const size_t xsz = (size_t)tc_size(xt);
-            GB_TRY(dmalloc(&u_perm, (size_t)c.hused * xsz + 16, err));
-            if (c.hused > 0) { spmv_permute_u(c.hperm, uval, u_perm, (int)xsz, c.hused); }
-            a.col = c.hcol; a.uval = u_perm;
-            g_hot.on = true; g_hot.hused = c.hused; g_hot.table_bytes = (size_t)atoi(hot_env) << 10;
-            if (const char *e = getenv("B200GRB_HOT_GROUPS")) g_hot.groups = atoi(e); else g_hot.groups = 4;
-        }
-        if (SPMV_PHASE_TIMERS && getenv("B200GRB_SPMV_DEBUG")) { GB_TRY(dalloc(&a.dbg, 8, err)); CU_TRY(cudaMemsetAsync(a.dbg, 0, 64, G.stream), err); }
+        if (SPMV_PHASE_TIMERS && tn.spmv_debug) { GB_TRY(dalloc(&a.dbg, 8, err)); CU_TRY(cudaMemsetAsync(a.dbg, 0, 64, G.stream), err); }
         GrB_Info r = spmv_dispatch(xt, zt, add, kmul, sparse_u, a, err);
         if (a.dbg) {
             unsigned long long h[5];
@@ -602,11 +506,10 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
                               (double)h[0] / h[4], (double)h[1] / h[4], (double)h[2] / h[4], (double)h[3] / h[4], h[4]);
             dfree(a.dbg);
         }
-        g_hot.on = false;
-        dfree(u_perm);
         dfree(a.head_val); dfree(a.tail_val); dfree(a.head_has); dfree(a.tail_has); dfree(a.tail_row);
         if (r != GrB_SUCCESS) { dfree(tval); dfree(tpres); dfree(a_cast); dfree(u_cast); return r; }
     }
+    if (burble.on) burble.note(kernel_name, (double)c.nnz * (4.0 + (need_a ? tc_size(xt) : 0)) + (double)(c.nrows + 1) * 4 + (double)c.ncols * (need_u ? tc_size(xt) : 0) + (double)n * (zsz + 1));
     dfree(a_cast); dfree(u_cast);
 
     // ---- w<mask> = accum(w, t)   (vector_ops.cu)

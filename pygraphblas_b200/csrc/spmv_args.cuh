@@ -15,6 +15,13 @@ struct RunArgs {
     uint8_t *tpres; uint8_t *head_has; uint8_t *tail_has;      // ... and of everything they produce
 };
 
+// hot-table run kernel (spmv_run.cuh)
+struct Hot2Args {
+    const void *u_hot;        // [henc] u at the hottest columns (prep kernel)
+    uint32_t henc;            // ids below this are hot ranks
+    uint32_t tab_n;           // entries of u_hot kept in shared memory (<= henc)
+};
+
 // ------------------------------------------------------------------ masked pull with early exit (BFS-shaped calls)
 // w<mask> = A (+).(x) u for monoids with a terminal value (LOR, LAND, ANY): one warp per row, rows the mask
 // rules out are skipped entirely (their entries are never read), and a row stops as soon as its monoid

@@ -76,8 +76,9 @@ static inline int hgrid(int64_t n) { return (int)std::max<int64_t>(1, std::min<i
 struct RunArgs;
 GrB_Info spmv_run_plan(Csr &c, std::string *err);
 GrB_Info spmv_hot_plan(Csr &c, std::string *err);
-void spmv_permute_u(const uint32_t *perm, const void *u, void *out, int vsize, int64_t n);
-bool spmv_run_dispatch(int xt, int add, int mul, const RunArgs &a, size_t hot_bytes, int64_t hused);
+struct Hot2Args;
+void spmv_hot2_prep(const Csr &c, const void *u, int vsize, void *tval, size_t tval_bytes, uint8_t *tpres);
+bool spmv_run_dispatch(int xt, int add, int mul, const RunArgs &a, const Hot2Args *hot, size_t table_limit);
 bool spmv_run_generic(int xt, int zt, const RunArgs &a);
 
 // ---- masked pull kernels (spmv_pull.cu)

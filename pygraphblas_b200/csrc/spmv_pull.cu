@@ -260,7 +260,7 @@ GrB_Info spmv_masked_push_try(int xt, int zt, PushArgs &a, int64_t nnz_total, bo
     CU_TRY(cudaStreamSynchronize(G.stream), err);
     const int64_t count = (int64_t)h[0], edges = (int64_t)h[1];
     // push pays per frontier vertex and per frontier edge, pull per unmasked row: push only small frontiers
-    if ((edges * 16 > nnz_total || count * 32 > a.nin) && getenv("B200GRB_FORCE_PUSH") == nullptr) { dfree(a.counters); return GrB_SUCCESS; }
+    if ((edges * 16 > nnz_total || count * 32 > a.nin) && !tunables().force_push) { dfree(a.counters); return GrB_SUCCESS; }
     GB_TRY(dalloc(&a.list, (size_t)count + 1, err));
     if (count > 0) {
         const int gf = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(a.nin, 256), (int64_t)G.num_sms * 16));

@@ -2,23 +2,6 @@
 #include "spmv_run.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
-// u_perm[i] = u[perm[i]]  (element size 1/2/4/8)
-__global__ void permute_u_kernel(const uint32_t *perm, const uint8_t *u, uint8_t *out, int vsize, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t c = perm[i];
-        switch (vsize) {
-            case 1: out[i] = u[c]; break;
-            case 2: ((uint16_t *)out)[i] = ((const uint16_t *)u)[c]; break;
-            case 4: ((uint32_t *)out)[i] = ((const uint32_t *)u)[c]; break;
-            default: ((uint64_t *)out)[i] = ((const uint64_t *)u)[c]; break;
-        }
-    }
-}
-
-void spmv_permute_u(const uint32_t *perm, const void *u, void *out, int vsize, int64_t n) {
-    if (n > 0) { permute_u_kernel<<<hgrid(n), 256, 0, G.stream>>>(perm, (const uint8_t *)u, (uint8_t *)out, vsize, n); GB_LAUNCHED(); }
-}
-
 // ---- run plan (cached per CSR)
 __global__ void plan_nonempty_kernel(const uint32_t *rowptr, int64_t nrows, int64_t *flag, uint8_t *pres) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
@@ -93,83 +76,121 @@ GrB_Info spmv_run_plan(Csr &c, std::string *err) {
     plan_base_kernel<<<rgrid(c.nruns + 1), 256, 0, G.stream>>>(cnt, c.nruns, c.run_base); GB_LAUNCHED();
     plan_tails_kernel<<<rgrid(c.nruns), 256, 0, G.stream>>>(c.run_base, c.nzrow, c.rowptr32, c.nruns, c.run_tail_row, c.run_tail_last); GB_LAUNCHED();
     dfree(flag); dfree(cnt);
+    // per-call scratch lives with the plan: partials of the rows that straddle runs (8 bytes covers every type)
+    GB_TRY(dmalloc(&c.ws_head, (size_t)c.nruns * 8 + 16, err));
+    GB_TRY(dmalloc(&c.ws_tail, (size_t)c.nruns * 8 + 16, err));
+    GB_TRY(dmalloc((void **)&c.ws_head_has, (size_t)c.nruns + 16, err));
+    GB_TRY(dmalloc((void **)&c.ws_tail_has, (size_t)c.nruns + 16, err));
     CU_TRY(cudaGetLastError(), err);
     return GrB_SUCCESS;
 }
 
-// ---- hot-column plan: relabel the columns by descending in-degree (cached per CSR)
+// ---- hot-column plan (cached per CSR): the HOT_ENC most referenced columns are renamed to their rank, every other
+//      column c to c + henc, so the kernel tells a table lookup from a gather of u by one compare and u itself is
+//      read in place (no permuted copy per call)
+constexpr uint32_t HOT_ENC = 40960;
 __global__ void hot_count_kernel(const uint32_t *col, int64_t nnz, uint32_t *deg) {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) atomicAdd(&deg[col[k]], 1u);
 }
 __global__ void hot_iota_kernel(uint32_t *a, int64_t n) {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) a[k] = (uint32_t)k;
 }
-__global__ void hot_invert_kernel(const uint32_t *perm, const uint32_t *deg_sorted, int64_t n, uint32_t *inv, unsigned long long *used) {
-    unsigned long long c = 0;
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
-        inv[perm[k]] = (uint32_t)k; c += deg_sorted[k] != 0;
+// inv[col] = rank for the first k ranks whose degree is non-zero; sum of their degrees; how many there are
+__global__ void hot_invert_kernel(const uint32_t *perm, const uint32_t *deg_sorted, int64_t k, uint32_t *inv, unsigned long long *stats) {
+    unsigned long long c = 0, d = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (int64_t)gridDim.x * blockDim.x) {
+        if (deg_sorted[i] != 0) { inv[perm[i]] = (uint32_t)i; c += 1; d += deg_sorted[i]; }
     }
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(used, c);
+    for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, o); d += __shfl_xor_sync(0xffffffffu, d, o); }
+    if ((threadIdx.x & 31) == 0 && c) { atomicAdd(stats, c); atomicAdd(stats + 1, d); }
 }
-__global__ void hot_cover_kernel(const uint32_t *deg_sorted, int64_t k, unsigned long long *sum) {
-    unsigned long long c = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (int64_t)gridDim.x * blockDim.x) c += deg_sorted[i];
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(sum, c);
-}
-__global__ void hot_relabel_kernel(const uint32_t *col, const uint32_t *inv, int64_t nnz, uint32_t *out) {
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) out[k] = inv[col[k]];
+__global__ void hot_encode_kernel(const uint32_t *col, const uint32_t *inv, int64_t nnz, uint32_t henc, uint32_t *out) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = col[k], r = inv[c];
+        out[k] = r < henc ? r : c + henc;
+    }
 }
 
 GrB_Info spmv_hot_plan(Csr &c, std::string *err) {
-    if (c.hcol) return GrB_SUCCESS;
+    if (c.hot_planned) return GrB_SUCCESS;
     const int64_t n = c.ncols;
-    uint32_t *deg = nullptr, *deg_sorted = nullptr, *ids = nullptr, *inv = nullptr; unsigned long long *used = nullptr;
+    if (n + (int64_t)HOT_ENC >= ((int64_t)1 << 32)) { c.hot_planned = true; return GrB_SUCCESS; }
+    uint32_t *deg = nullptr, *deg_sorted = nullptr, *ids = nullptr, *inv = nullptr, *perm = nullptr; unsigned long long *stats = nullptr;
     GB_TRY(dalloc(&deg, (size_t)n, err)); GB_TRY(dalloc(&deg_sorted, (size_t)n, err)); GB_TRY(dalloc(&ids, (size_t)n, err));
-    GB_TRY(dalloc(&inv, (size_t)n, err)); GB_TRY(dalloc(&used, 2, err));
-    GB_TRY(dalloc(&c.hperm, (size_t)n, err));
-    GB_TRY(dalloc(&c.hcol, (size_t)c.nnz, err));
+    GB_TRY(dalloc(&inv, (size_t)n, err)); GB_TRY(dalloc(&perm, (size_t)n, err)); GB_TRY(dalloc(&stats, 2, err));
     CU_TRY(cudaMemsetAsync(deg, 0, (size_t)n * 4, G.stream), err);
-    CU_TRY(cudaMemsetAsync(used, 0, 16, G.stream), err);
+    CU_TRY(cudaMemsetAsync(inv, 0xff, (size_t)n * 4, G.stream), err);
+    CU_TRY(cudaMemsetAsync(stats, 0, 16, G.stream), err);
     hot_count_kernel<<<hgrid(c.nnz), 256, 0, G.stream>>>(c.col, c.nnz, deg); GB_LAUNCHED();
     hot_iota_kernel<<<hgrid(n), 256, 0, G.stream>>>(ids, n); GB_LAUNCHED();
     size_t tmp_bytes = 0;     // stable sort: equal degrees keep ascending column order (deterministic plan)
-    CU_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, deg, deg_sorted, ids, c.hperm, n, 0, 32, G.stream), err);
+    CU_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, deg, deg_sorted, ids, perm, n, 0, 32, G.stream), err);
     void *tmp = nullptr; GB_TRY(dmalloc(&tmp, tmp_bytes, err));
-    CU_TRY(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, deg, deg_sorted, ids, c.hperm, n, 0, 32, G.stream), err);
+    CU_TRY(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, deg, deg_sorted, ids, perm, n, 0, 32, G.stream), err);
     G.launches += 8;
-    hot_invert_kernel<<<hgrid(n), 256, 0, G.stream>>>(c.hperm, deg_sorted, n, inv, used); GB_LAUNCHED();
-    hot_relabel_kernel<<<hgrid(c.nnz), 256, 0, G.stream>>>(c.col, inv, c.nnz, c.hcol); GB_LAUNCHED();
-    const int64_t topk = std::min<int64_t>(n, 40960);
-    hot_cover_kernel<<<hgrid(topk), 256, 0, G.stream>>>(deg_sorted, topk, used + 1); GB_LAUNCHED();
+    const int64_t topk = std::min<int64_t>(n, HOT_ENC);
+    hot_invert_kernel<<<hgrid(topk), 256, 0, G.stream>>>(perm, deg_sorted, topk, inv, stats); GB_LAUNCHED();
     unsigned long long h[2] = {0, 0};
-    CU_TRY(cudaMemcpyAsync(h, used, 16, cudaMemcpyDeviceToHost, G.stream), err);
+    CU_TRY(cudaMemcpyAsync(h, stats, 16, cudaMemcpyDeviceToHost, G.stream), err);
     CU_TRY(cudaStreamSynchronize(G.stream), err);
-    c.hused = (int64_t)h[0];
     c.hot_cover = c.nnz ? (double)h[1] / (double)c.nnz : 0.0;
-    dfree(tmp); dfree(deg); dfree(deg_sorted); dfree(ids); dfree(inv); dfree(used);
+    c.hot_planned = true;
+    if (h[0] >= 16) {
+        c.henc = (uint32_t)h[0];
+        GB_TRY(dalloc(&c.hperm, (size_t)c.henc, err));
+        GB_TRY(dalloc(&c.hcol, (size_t)c.nnz, err));
+        GB_TRY(dmalloc(&c.ws_uhot, (size_t)c.henc * 8 + 16, err));
+        CU_TRY(cudaMemcpyAsync(c.hperm, perm, (size_t)c.henc * 4, cudaMemcpyDeviceToDevice, G.stream), err);
+        hot_encode_kernel<<<hgrid(c.nnz), 256, 0, G.stream>>>(c.col, inv, c.nnz, c.henc, c.hcol); GB_LAUNCHED();
+    }
+    dfree(tmp); dfree(deg); dfree(deg_sorted); dfree(ids); dfree(inv); dfree(perm); dfree(stats);
+    CU_TRY(cudaGetLastError(), err);
     return GrB_SUCCESS;
 }
 
+// prep for the hot-table kernel, one launch: u_hot[i] = u[hperm[i]] for the henc hottest columns, T's values
+// cleared and its presence bytes set from the plan's template (rows are structurally present or not: u is dense)
+__global__ void __launch_bounds__(256) spmv_hot2_prep_kernel(const uint32_t *hperm, const uint8_t *u, uint8_t *u_hot, int vsize, uint32_t henc,
+                                                            uint4 *tval16, int64_t tval_n16, const uint4 *tmpl16, uint4 *tpres16, int64_t pres_n16) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < henc; i += nth) {
+        const uint32_t col = hperm[i];
+        switch (vsize) {
+            case 1: u_hot[i] = u[col]; break;
+            case 4: ((uint32_t *)u_hot)[i] = ((const uint32_t *)u)[col]; break;
+            default: ((uint64_t *)u_hot)[i] = ((const uint64_t *)u)[col]; break;
+        }
+    }
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int64_t i = tid; i < tval_n16; i += nth) tval16[i] = z;
+    for (int64_t i = tid; i < pres_n16; i += nth) tpres16[i] = tmpl16[i];
+}
 
-template <typename T> static bool spmv_run_fast(int add, int mul, const RunArgs &a, size_t hot_bytes, int64_t hused) {
-#define GB_FAST(A, M) if (add == A && mul == M) { spmv_run_launch<T, T, A, M>(a, hot_bytes, hused); return true; }
+// one launch ahead of the hot-table kernel: u at the hot columns, T cleared, T's presence from the plan's template
+void spmv_hot2_prep(const Csr &c, const void *u, int vsize, void *tval, size_t tval_bytes, uint8_t *tpres) {
+    const int64_t tv16 = (int64_t)((tval_bytes + 15) / 16), pr16 = (c.nrows + 15) / 16;      // buffers are padded by >= 16 bytes
+    spmv_hot2_prep_kernel<<<G.num_sms * 8, 256, 0, G.stream>>>(c.hperm, (const uint8_t *)u, (uint8_t *)c.ws_uhot, vsize, c.henc,
+                                                               (uint4 *)tval, tv16, (const uint4 *)c.pres_tmpl, (uint4 *)tpres, pr16);
+    GB_LAUNCHED();
+}
+
+template <typename T> static bool spmv_run_fast(int add, int mul, const RunArgs &a, const Hot2Args *hot, size_t table_limit) {
+#define GB_FAST(A, M) if (add == A && mul == M) { spmv_run_launch<T, T, A, M>(a, hot, table_limit); return true; }
     GB_FAST(OP_PLUS, OP_TIMES) GB_FAST(OP_MIN, OP_PLUS) GB_FAST(OP_PLUS, OP_SECOND) GB_FAST(OP_PLUS, OP_FIRST)
     GB_FAST(OP_PLUS, OP_PAIR) GB_FAST(OP_MIN, OP_FIRST) GB_FAST(OP_MIN, OP_SECOND)
 #undef GB_FAST
     return false;
 }
-bool spmv_run_fast_int(int xt, int add, int mul, const RunArgs &a, size_t hot_bytes, int64_t hused);
-bool spmv_run_dispatch(int xt, int add, int mul, const RunArgs &a, size_t hot_bytes, int64_t hused) {
+bool spmv_run_fast_int(int xt, int add, int mul, const RunArgs &a, const Hot2Args *hot, size_t table_limit);
+bool spmv_run_dispatch(int xt, int add, int mul, const RunArgs &a, const Hot2Args *hot, size_t table_limit) {
     switch (xt) {
-        case TC_FP32: return spmv_run_fast<float>(add, mul, a, hot_bytes, hused);
-        case TC_FP64: return spmv_run_fast<double>(add, mul, a, hot_bytes, hused);
+        case TC_FP32: return spmv_run_fast<float>(add, mul, a, hot, table_limit);
+        case TC_FP64: return spmv_run_fast<double>(add, mul, a, hot, table_limit);
         case TC_INT32:
         case TC_INT64:
         case TC_UINT32:
         case TC_UINT64:
-        case TC_BOOL: return spmv_run_fast_int(xt, add, mul, a, hot_bytes, hused);
+        case TC_BOOL: return spmv_run_fast_int(xt, add, mul, a, hot, table_limit);
         default: return false;
     }
 }

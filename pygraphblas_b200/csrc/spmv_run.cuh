@@ -18,28 +18,19 @@
 // HOT: persistent CTAs, hot_n most referenced entries of the (relabelled) u in a shared-memory table.
 
 
-template <typename XT, typename ZT, int ADD_C, int MUL_C, bool HOT, bool SPARSE = false>
-__device__ __forceinline__ void spmv_run_body(const RunArgs &p, const int64_t run, const int lane, const XT *s_hot, const uint32_t hot_n) {
+// Everything after a lane holds its 8 column ids / values: gather u, fold between the row-start bits, scan, store.
+// `gather(c)` returns u's value for an (encoded) column id of a dense u; SPARSE kernels read p.uval / p.upres directly.
+template <typename XT, typename ZT, int ADD_C, int MUL_C, bool SPARSE, typename Gather>
+__device__ __forceinline__ void spmv_run_finish(const RunArgs &p, const int64_t run, const int lane, const int nvalid,
+                                                uint32_t (&c)[8], XT (&a)[8], Gather &&gather) {
     // ADD_C / MUL_C >= 0: compile-time semiring; -1: run-time operator codes (both operands are read)
     constexpr bool NEED_A = MUL_C < 0 || mul_reads_x(MUL_C);
     constexpr bool NEED_U = MUL_C < 0 || mul_reads_y(MUL_C);
     const int ADD = ADD_C >= 0 ? ADD_C : p.add_op;
     const int MUL = MUL_C >= 0 ? MUL_C : p.mul_op;
     const int64_t q = run * RUN + lane * 8;
-    const int nvalid = (int)min((int64_t)8, max((int64_t)0, p.nnz - q));
     const XT *uval = static_cast<const XT *>(p.uval);
     ZT *tval = static_cast<ZT *>(p.tval);
-    uint32_t c[8]; XT a[8];
-    if (nvalid == 8) {
-        load4<uint32_t>(p.col + q, &c[0]); load4<uint32_t>(p.col + q + 4, &c[4]);
-        if (NEED_A) { load4<XT>(static_cast<const XT *>(p.aval) + q, &a[0]); load4<XT>(static_cast<const XT *>(p.aval) + q + 4, &a[4]); }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            c[j] = j < nvalid ? p.col[q + j] : 0u;
-            if (NEED_A) a[j] = j < nvalid ? static_cast<const XT *>(p.aval)[q + j] : (XT)1;
-        }
-    }
     const uint32_t hw = nvalid > 0 ? __ldg(p.headw + (q >> 5)) : 0u;
     const uint32_t hb = (hw >> ((lane & 3) * 8)) & 0xffu;                 // this lane's 8 row-start bits
     uint32_t rank = __ldg(p.run_base + run) + __ldg(p.lane_rank + run * 32 + lane);   // row starts before this lane's first entry
@@ -52,10 +43,7 @@ __device__ __forceinline__ void spmv_run_body(const RunArgs &p, const int64_t ru
         for (int j = 0; j < 8; ++j) uv[j] = (NEED_U && up[j]) ? gload<XT>(uval + c[j]) : (XT)0;
     } else if (NEED_U) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (HOT && c[j] < hot_n) uv[j] = s_hot[c[j]];
-            else uv[j] = gload<XT>(uval + c[j]);
-        }
+        for (int j = 0; j < 8; ++j) uv[j] = gather(c[j]);
     }
     ZT prod[8];
 #pragma unroll
@@ -119,23 +107,150 @@ __device__ __forceinline__ void spmv_run_body(const RunArgs &p, const int64_t ru
     }
 }
 
+// ---- plain run kernel: 8 warps per CTA, each warp streams its run straight from global memory into registers
+template <typename XT, typename ZT, int MUL_C>
+__device__ __forceinline__ int spmv_run_load_global(const RunArgs &p, const int64_t run, const int lane, uint32_t (&c)[8], XT (&a)[8]) {
+    constexpr bool NEED_A = MUL_C < 0 || mul_reads_x(MUL_C);
+    const int64_t q = run * RUN + lane * 8;
+    const int nvalid = (int)min((int64_t)8, max((int64_t)0, p.nnz - q));
+    if (nvalid == 8) {
+        load4<uint32_t>(p.col + q, &c[0]); load4<uint32_t>(p.col + q + 4, &c[4]);
+        if (NEED_A) { load4<XT>(static_cast<const XT *>(p.aval) + q, &a[0]); load4<XT>(static_cast<const XT *>(p.aval) + q + 4, &a[4]); }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            c[j] = j < nvalid ? p.col[q + j] : 0u;
+            if (NEED_A) a[j] = j < nvalid ? static_cast<const XT *>(p.aval)[q + j] : (XT)1;
+        }
+    }
+    return nvalid;
+}
+
 template <typename XT, typename ZT, int ADD, int MUL, bool SPARSE>
 __global__ void __launch_bounds__(256) spmv_run_kernel(const RunArgs p) {
     const int64_t run = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (run >= p.nruns) return;
-    spmv_run_body<XT, ZT, ADD, MUL, false, SPARSE>(p, run, threadIdx.x & 31, nullptr, 0u);
+    const int lane = threadIdx.x & 31;
+    uint32_t c[8]; XT a[8];
+    const int nvalid = spmv_run_load_global<XT, ZT, MUL>(p, run, lane, c, a);
+    const XT *uval = static_cast<const XT *>(p.uval);
+    spmv_run_finish<XT, ZT, ADD, MUL, SPARSE>(p, run, lane, nvalid, c, a, [uval](uint32_t col) { return gload<XT>(uval + col); });
 }
 
-template <typename XT, typename ZT, int ADD, int MUL, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) spmv_run_hot_kernel(const RunArgs p, const uint32_t hot_n) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    XT *s_hot = reinterpret_cast<XT *>(smem_raw);
-    const XT *uval = static_cast<const XT *>(p.uval);
-    for (uint32_t i = threadIdx.x; i < hot_n; i += blockDim.x) s_hot[i] = uval[i];
+// ==================================================================================================
+// Hot-table run kernel (dense u, specialised semirings, large skewed matrices) -- the benchmarked kernel.
+//
+// One persistent 1024-thread CTA per SM.  Shared memory holds
+//   * the HOT TABLE: u at the tab_n most referenced columns (a scattered 4-byte gather costs one L1 wavefront
+//     per lane; a shared-memory lookup a few bank-conflict cycles per warp), filled once per CTA by bulk TMA
+//     copies (cp.async.bulk -> SASS UBLKCP) from the gathered copy u_hot that the prep kernel writes;
+//   * one STAGE per warp: the column ids and values of the warp's NEXT run, brought in by two bulk TMA copies
+//     issued by lane 0 and completed on the warp's own mbarrier, so the DRAM stream of run r+1 is in flight
+//     while the warp gathers and folds run r (registers are the second buffer: a run is copied out of the
+//     stage before the next copy is issued).  A warp is its own producer and consumer: no CTA barrier after
+//     the table is in.
+// Column ids are ENCODED by the cached plan: id < henc -> rank among the hottest columns (table if < tab_n,
+// else u_hot in L2); id >= henc -> original column + henc, gathered from u itself.  u needs no permutation.
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <typename XT> __host__ __device__ constexpr int hot2_stage_bytes(bool need_a) { return RUN * 4 + (need_a ? RUN * (int)sizeof(XT) : 0); }
+constexpr int HOT2_WARPS = 32;
+
+template <typename XT, typename ZT, int ADD, int MUL>
+__global__ void __launch_bounds__(HOT2_WARPS * 32, 1) spmv_run_hot2_kernel(const RunArgs p, const Hot2Args h) {
+    constexpr bool NEED_A = mul_reads_x(MUL);
+    constexpr int STAGE = hot2_stage_bytes<XT>(NEED_A);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: [warp stages][mbarriers][hot table]
+    unsigned char *s_stage = smem_raw;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + HOT2_WARPS * STAGE);        // [HOT2_WARPS] per warp + [1] table
+    XT *s_hot = reinterpret_cast<XT *>(smem_raw + HOT2_WARPS * STAGE + (HOT2_WARPS + 1) * 8 + 8);   // 16-byte aligned
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *bar = s_bar + warp;
+    unsigned char *stage = s_stage + warp * STAGE;
+    const int64_t stride = (int64_t)gridDim.x * HOT2_WARPS;
+    int64_t run = (int64_t)blockIdx.x * HOT2_WARPS + warp;
+
+    auto issue = [&](int64_t r) {             // lane 0: the bulk copies of run r into this warp's stage
+        const int64_t q = r * RUN;
+        const int64_t left = p.nnz - q;
+        const uint32_t cnt = (uint32_t)(left < RUN ? left : RUN);
+        const uint32_t cb = (cnt * 4u + 15u) & ~15u;                                      // arrays are padded by >= 16 bytes
+        const uint32_t ab = NEED_A ? ((cnt * (uint32_t)sizeof(XT) + 15u) & ~15u) : 0u;
+        mbar_expect_tx(bar, cb + ab);
+        tma_bulk_g2s(stage, p.col + q, cb, bar);
+        if (NEED_A) tma_bulk_g2s(stage + RUN * 4, static_cast<const XT *>(p.aval) + q, ab, bar);
+    };
+
+    if (lane == 0) mbar_init(bar, 1);
+    if (threadIdx.x == 0) mbar_init(s_bar + HOT2_WARPS, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    const int warps = blockDim.x >> 5;
-    for (int64_t run = (int64_t)blockIdx.x * warps + (threadIdx.x >> 5); run < p.nruns; run += (int64_t)gridDim.x * warps)
-        spmv_run_body<XT, ZT, ADD, MUL, true>(p, run, threadIdx.x & 31, s_hot, hot_n);
+    if (threadIdx.x == 0 && h.tab_n) {        // the table: bulk copies of <= 16 KB
+        const uint32_t total = h.tab_n * (uint32_t)sizeof(XT);
+        mbar_expect_tx(s_bar + HOT2_WARPS, total);
+        for (uint32_t off = 0; off < total; off += 16384u)
+            tma_bulk_g2s(reinterpret_cast<unsigned char *>(s_hot) + off, static_cast<const unsigned char *>(h.u_hot) + off,
+                         min(16384u, total - off), s_bar + HOT2_WARPS);
+    }
+    if (lane == 0 && run < p.nruns) issue(run);
+    if (h.tab_n) mbar_wait(s_bar + HOT2_WARPS, 0);
+
+    const XT *uval = static_cast<const XT *>(p.uval);
+    const XT *uhot = static_cast<const XT *>(h.u_hot);
+    const uint32_t tab_n = h.tab_n, henc = h.henc;
+    auto gather = [=](uint32_t col) -> XT {
+        if (col < tab_n) return s_hot[col];
+        if (col < henc) return gload<XT>(uhot + col);
+        return gload<XT>(uval + (col - henc));
+    };
+    uint32_t parity = 0;
+    for (; run < p.nruns; run += stride) {
+        mbar_wait(bar, parity); parity ^= 1u;
+        const int64_t q = run * RUN + lane * 8;
+        const int nvalid = (int)min((int64_t)8, max((int64_t)0, p.nnz - q));
+        uint32_t c[8]; XT a[8];
+        {
+            const uint4 *sc = reinterpret_cast<const uint4 *>(stage) + lane * 2;
+            const uint4 c0 = sc[0], c1 = sc[1];
+            c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+            if (NEED_A) {
+                const XT *sa = reinterpret_cast<const XT *>(stage + RUN * 4) + lane * 8;
+                if constexpr (sizeof(XT) == 4) {
+                    const uint4 a0 = reinterpret_cast<const uint4 *>(sa)[0], a1 = reinterpret_cast<const uint4 *>(sa)[1];
+                    const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] = reinterpret_cast<const XT &>(w[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] = sa[j];
+                }
+            }
+            if (nvalid < 8) {                                                   // tail of the last run: what lies past nnz is not data
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { if (j >= nvalid) { c[j] = henc; if (NEED_A) a[j] = (XT)1; } }
+            }
+        }
+        __syncwarp();                                                           // every lane has its words: the stage is free
+        if (lane == 0 && run + stride < p.nruns) issue(run + stride);
+        spmv_run_finish<XT, ZT, ADD, MUL, false>(p, run, lane, nvalid, c, a, gather);
+    }
 }
 
 // rows that continue past their run: tail partial (+) head partials of the following runs, 8 lanes per open row.
@@ -163,30 +278,37 @@ __global__ void __launch_bounds__(256) spmv_run_fixup_kernel(const RunArgs p) {
     if (r >= 0 && sub == 0) { static_cast<ZT *>(p.tval)[r] = acc.v; if (SPARSE) p.tpres[r] = (uint8_t)acc.has; }
 }
 
+// shared memory the hot-table kernel can use for its table, after the warp stages and barriers
+template <typename XT> static inline uint32_t hot2_table_entries(bool need_a, uint32_t henc, size_t limit_bytes) {
+    int max_optin = 0;
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, G.device);
+    const size_t fixed = (size_t)HOT2_WARPS * hot2_stage_bytes<XT>(need_a) + (HOT2_WARPS + 1) * 8 + 8;
+    size_t avail = (size_t)max_optin > fixed + 256 ? (size_t)max_optin - fixed - 256 : 0;
+    avail = std::min(avail, limit_bytes);
+    return (uint32_t)std::min<size_t>(henc, avail / sizeof(XT)) & ~15u;
+}
+
 template <typename XT, typename ZT, int ADD, int MUL>
-static void spmv_run_launch(const RunArgs &a, size_t hot_bytes, int64_t hused) {
-    if (hot_bytes && ADD >= 0 && !a.upres) {
-        // two shapes: one 1024-thread CTA per SM with a table of up to ~200 KB, or two 768-thread CTAs
-        // per SM (<= 42 registers) with a table of up to ~100 KB each
-        const bool two = hot_bytes <= ((size_t)104 << 10) && getenv("B200GRB_HOT_ONE") == nullptr;
-        const uint32_t hot_n = (uint32_t)std::min<int64_t>(hused, (int64_t)(hot_bytes / sizeof(XT)));
-        const size_t smem = (size_t)hot_n * sizeof(XT);
-        if (two) {
-            auto kernel = spmv_run_hot_kernel<XT, ZT, ADD, MUL, 768, 2>;
+static void spmv_run_launch(const RunArgs &a, const Hot2Args *hot, size_t table_limit) {
+    if constexpr (ADD >= 0) {
+        if (hot && !a.upres) {
+            constexpr bool NEED_A = mul_reads_x(MUL);
+            Hot2Args h = *hot;
+            h.tab_n = hot2_table_entries<XT>(NEED_A, h.henc, table_limit);
+            const size_t smem = (size_t)HOT2_WARPS * hot2_stage_bytes<XT>(NEED_A) + (HOT2_WARPS + 1) * 8 + 8 + (size_t)h.tab_n * sizeof(XT);
+            auto kernel = spmv_run_hot2_kernel<XT, ZT, ADD, MUL>;
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            kernel<<<G.num_sms * 2, 768, smem, G.stream>>>(a, hot_n); GB_LAUNCHED();
-        } else {
-            auto kernel = spmv_run_hot_kernel<XT, ZT, ADD, MUL, 1024, 1>;
-            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            kernel<<<G.num_sms, 1024, smem, G.stream>>>(a, hot_n); GB_LAUNCHED();
+            const int ctas = (int)std::min<int64_t>(G.num_sms, ceil_div(a.nruns, HOT2_WARPS));
+            kernel<<<ctas, HOT2_WARPS * 32, smem, G.stream>>>(a, h); GB_LAUNCHED();
+            spmv_run_fixup_kernel<ZT, ADD, false><<<(unsigned)ceil_div(a.nruns * 8, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED();
+            return;
         }
-    } else if (a.upres) {
+    }
+    if (a.upres) {
         spmv_run_kernel<XT, ZT, ADD, MUL, true><<<(unsigned)ceil_div(a.nruns, 8), 256, 0, G.stream>>>(a); GB_LAUNCHED();
         spmv_run_fixup_kernel<ZT, ADD, true><<<(unsigned)ceil_div(a.nruns * 8, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED();
         return;
-    } else {
-        spmv_run_kernel<XT, ZT, ADD, MUL, false><<<(unsigned)ceil_div(a.nruns, 8), 256, 0, G.stream>>>(a); GB_LAUNCHED();
     }
+    spmv_run_kernel<XT, ZT, ADD, MUL, false><<<(unsigned)ceil_div(a.nruns, 8), 256, 0, G.stream>>>(a); GB_LAUNCHED();
     spmv_run_fixup_kernel<ZT, ADD, false><<<(unsigned)ceil_div(a.nruns * 8, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED();
 }
-

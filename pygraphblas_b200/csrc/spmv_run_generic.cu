@@ -2,7 +2,7 @@
 #include "spmv_run.cuh"
 
 bool spmv_run_generic(int xt, int zt, const RunArgs &a) {
-#define GB_RUNGEN(XT_, ZT_) do { spmv_run_launch<XT_, ZT_, -1, -1>(a, 0, 0); return true; } while (0)
+#define GB_RUNGEN(XT_, ZT_) do { spmv_run_launch<XT_, ZT_, -1, -1>(a, nullptr, 0); return true; } while (0)
     if (xt == zt) {
         switch (xt) {
 #define GB_GEN(TC, T) case TC: GB_RUNGEN(T, T);

@@ -24,6 +24,7 @@ def run(label, sr, env):
     if keep_run is not None and "B200GRB_SPMV_RUN" not in env:
         os.environ["B200GRB_SPMV_RUN"] = keep_run
     os.environ.update(env)
+    gb.lib.B200_reload_tunables()
     for _ in range(5):
         A.mxv(u, semiring=sr, out=w)
     gb.lib.B200_device_synchronize()
@@ -36,11 +37,11 @@ def run(label, sr, env):
     ms = e0.elapsed_time(e1) / 30
     print(f"{label:44s} {ms*1e3:8.1f} us", flush=True)
 
-run("run kernel PLUS_TIMES", FP32.PLUS_TIMES, {})
+run("default (hot table, TMA staged) PLUS_TIMES", FP32.PLUS_TIMES, {})
 run("run kernel PLUS_SECOND", FP32.PLUS_SECOND, {})
 run("run kernel PLUS_FIRST (no gather)", FP32.PLUS_FIRST, {})
 run("run kernel PLUS_PAIR (col only)", FP32.PLUS_PAIR, {})
 run("run kernel MIN_PLUS", FP32.MIN_PLUS, {})
-for kb in ("32", "64", "80", "96", "104", "128", "160"):
+for kb in ("0", "32", "64", "96", "128", "160"):
     run(f"run kernel + hot table {kb}KB PLUS_TIMES", FP32.PLUS_TIMES, {"B200GRB_SPMV_HOT": kb})
 run("run-time operators: PLUS_MINUS", FP32.PLUS_MINUS, {})
