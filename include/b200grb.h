@@ -221,6 +221,30 @@ uint64_t B200_kernel_launches(void);
 /* per-matrix SpGEMM/SpMV work figures of the most recent GrB_mxm (flops = number of
  * multiplies, nnz_out = nvals of the semiring product before accum/mask) */
 GrB_Info B200_last_mxm_stats(uint64_t *flops, uint64_t *nnz_out);
+/* ------------------------------------------------------------------ multi-GPU exchange (csrc/dist.cu)
+ * One process per GPU; A is 1-D row-block partitioned.  The library moves the output
+ * slices itself, with its own kernels over CUDA-IPC-mapped peer HBM (NVLink / NVSwitch): the host only carries
+ * the 64-byte IPC handles between the processes.  Replaces nothing in the reference (which is single-process,
+ * /root/reference/pygraphblas/matrix.py:2586-2726); it is the exchange step north_star asks for after GrB_mxv.  */
+typedef struct B200_Comm_opaque *B200_Comm;
+/* a communicator for replicated vectors of n values of `type` among `world` ranks (this process is `rank`) */
+GrB_Info B200_Comm_create(B200_Comm *comm, int rank, int world, GrB_Index n, GrB_Type type);
+/* this rank's 64-byte IPC handle; gather all ranks' handles (rank order) and pass them to connect */
+GrB_Info B200_Comm_handle(B200_Comm comm, void *handle64);
+GrB_Info B200_Comm_connect(B200_Comm comm, const void *all_handles);
+GrB_Info B200_Comm_free(B200_Comm *comm);
+/* all-gather: positions [row0, row0 + size(slice)) of the replicated vector := slice, on EVERY rank, for all ranks'
+ * slices (row0 a multiple of 16); enqueued on the library stream, complete (stream order) when it returns */
+GrB_Info B200_Comm_allgather(B200_Comm comm, const GrB_Vector slice, GrB_Index row0);
+/* all-reduce: every rank passes a full-length partial; the replicated vector := the monoid fold of the partials
+ * present at each position, taken in rank order (deterministic) */
+GrB_Info B200_Comm_allreduce(B200_Comm comm, const GrB_Vector partial, GrB_Monoid monoid);
+/* the replicated vector produced by the last collective, as a GrB_Vector that borrows the communicator's buffer
+ * (valid until the next collective on this communicator; usable as the input of GrB_mxv / GrB_vxm) */
+GrB_Info B200_Comm_result(B200_Comm comm, GrB_Vector *view);
+/* flags-only round: every rank has enqueued everything before this point */
+GrB_Info B200_Comm_barrier(B200_Comm comm);
+
 /* kernel-choice switches (B200GRB_* environment variables) are read once at GrB_init; re-read them now */
 GrB_Info B200_reload_tunables(void);
 /* same switch as GxB_Global_Option_set(GxB_BURBLE, on) (/root/reference/pygraphblas/base.py:84-86): every compute

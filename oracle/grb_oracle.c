@@ -311,7 +311,7 @@ int oracle_mxm(ores_t *out,
             const int64_t j = jc < jt ? jc : jt;
             const bool cp = jc == j, tp = jt == j;
             /* step 4: mask */
-            bool m = true;
+            bool m = !(d->mask_comp && !has_mask);   /* C<!NULL>: the complement of "no mask" lets nothing through (C API 1.3, 4.3) */
             if (has_mask) {
                 while (pm < pme && M.col[pm] < j) ++pm;
                 m = pm < pme && M.col[pm] == j;

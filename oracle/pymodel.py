@@ -125,7 +125,7 @@ def mxm(C, ctype, M, mtype, accum, semiring, A, atype, B, btype, desc):
 
     def m(k):
         if M is None:
-            return True
+            return not desc["mask_comp"]      # C<!NULL>: the complement of "no mask" lets nothing through (C API 1.3, 4.3)
         r = k in M and (desc["mask_struct"] or bool(cast(M[k], "BOOL")))
         return (not r) if desc["mask_comp"] else r
 

@@ -68,7 +68,7 @@ def write(w, wtype, mask, accum, T, ttype, desc, region=None, n=None):
 
     def m(k):
         if mask is None:
-            return True
+            return not desc.get("mask_comp", False)      # w<!NULL>: nothing is let through
         mv, _ = mask
         r = k in mv and (desc.get("mask_struct", False) or bool(cast(mv[k], "BOOL")))
         return (not r) if desc.get("mask_comp", False) else r

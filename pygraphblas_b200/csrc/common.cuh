@@ -114,6 +114,7 @@ struct GB_Vector_opaque {
     std::vector<uint64_t> pi; std::vector<uint8_t> px;
     // device form: dense values + presence bytes (present == nullptr: all present)
     void *dval = nullptr; uint8_t *dpres = nullptr; bool dev_valid = false; int64_t dev_nvals = -1;
+    bool borrowed = false;     // dval / dpres belong to a communicator (dist.cu): never freed through the vector
     std::string err;
 };
 

@@ -400,7 +400,8 @@ static const uint64_t DEV_DIM_MAX = ((uint64_t)1 << 31) - 1;   // 32-bit column 
 
 void matrix_invalidate_device(GrB_Matrix A) { csr_free(A->dev); csr_free(A->devT); }
 void vector_invalidate_device(GrB_Vector v) {
-    dfree(v->dval); dfree(v->dpres); v->dval = nullptr; v->dpres = nullptr; v->dev_valid = false; v->dev_nvals = -1;
+    if (!v->borrowed) { dfree(v->dval); dfree(v->dpres); }       // a borrowed view (B200_Comm_result) does not own its buffers
+    v->borrowed = false; v->dval = nullptr; v->dpres = nullptr; v->dev_valid = false; v->dev_nvals = -1;
 }
 void matrix_adopt_device(GrB_Matrix A, Csr &c) {
     matrix_invalidate_device(A);

@@ -1081,6 +1081,15 @@ static GrB_Info matrix_finalize(const Csr *C, int ctc, const Csr &T, int ttc, co
 GrB_Info matrix_writeback(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const DescFlags &f,
                           Csr &T, int ttc, bool t_already_masked, std::string *err) {
     const int ctc = C->type->code;
+    if (!Mask && f.mask_comp) {
+        // C<!NULL>: nothing is written; GrB_REPLACE clears C (C API 1.3 section 4.3, SuiteSparse's quick-mask exit)
+        csr_free(T);
+        if (f.replace) {
+            matrix_invalidate_device(C);
+            C->hi.clear(); C->hj.clear(); C->hx.clear(); C->pi.clear(); C->pj.clear(); C->px.clear(); C->host_valid = true;
+        }
+        return GrB_SUCCESS;
+    }
     const bool c_empty = C->host_valid ? (C->hi.empty() && C->pi.empty()) : (C->dev.nnz == 0);
     // fast exits: the result is exactly T
     const bool plain = !accum && (!Mask || (t_already_masked && (f.replace || c_empty)));
@@ -1124,6 +1133,8 @@ extern "C" GrB_Info GrB_mxm(GrB_Matrix C, const GrB_Matrix Mask, const GrB_Binar
     if (!G.have_device) return gb_fail(GrB_PANIC, err, "GrB_mxm: no CUDA device: libb200grb computes only on the GPU (no CPU fallback)");
     const int xt = mulop->xtype->code, zt = addop->ztype->code, add = addop->opcode, mul = mulop->opcode;
     const bool need_a = op_uses_x(mul), need_b = op_uses_y(mul);
+    GbBurble burble("GrB_mxm");
+    if (!Mask && f.mask_comp) { Csr none; return matrix_writeback(C, nullptr, accum, f, none, zt, false, err); }   // C<!NULL>: no product needed
 
     // masked methods apply to non-complemented masks
     const bool use_mask = Mask && !f.mask_comp;

@@ -377,6 +377,8 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
     if (!G.have_device) return gb_fail(GrB_PANIC, err, "%s: no CUDA device: libb200grb computes only on the GPU (no CPU fallback)", fn);
     const int xt = mulop->xtype->code, zt = addop->ztype->code;
     const int add = addop->opcode, mul = mulop->opcode;
+    if (!mask && f.mask_comp)      // w<!NULL>: nothing is let through, no product needed (vector_write clears w under REPLACE)
+        return vector_write(w, nullptr, accum, f, nullptr, nullptr, zt, false, nullptr, true);
 
     // ---- operands in HBM
     if (use_transpose) GB_TRY(matrix_ensure_transpose(A)); else GB_TRY(matrix_ensure_device(A));

@@ -18,37 +18,50 @@
 // HOT: persistent CTAs, hot_n most referenced entries of the (relabelled) u in a shared-memory table.
 
 
-// Everything after a lane holds its 8 column ids / values: gather u, fold between the row-start bits, scan, store.
+// A lane's share of a run in flight: its 8 matrix values, the 8 values of u it gathered (presence bytes for a sparse u),
+// its row-start bits and the rank of its first row start.
+template <typename XT> struct RunLane { XT a[8]; XT uv[8]; uint8_t up[8]; uint32_t hb; uint32_t rank; int nvalid; };
+
+// Part 1: everything that ISSUES loads -- the plan words of the lane and the gathers of u.
 // `gather(c)` returns u's value for an (encoded) column id of a dense u; SPARSE kernels read p.uval / p.upres directly.
-template <typename XT, typename ZT, int ADD_C, int MUL_C, bool SPARSE, typename Gather>
-__device__ __forceinline__ void spmv_run_finish(const RunArgs &p, const int64_t run, const int lane, const int nvalid,
-                                                uint32_t (&c)[8], XT (&a)[8], Gather &&gather) {
+template <typename XT, int MUL_C, bool SPARSE, typename Gather>
+__device__ __forceinline__ void spmv_run_gather(const RunArgs &p, const int64_t run, const int lane, const int nvalid,
+                                                const uint32_t (&c)[8], RunLane<XT> &L, Gather &&gather) {
+    constexpr bool NEED_U = MUL_C < 0 || mul_reads_y(MUL_C);
+    const int64_t q = run * RUN + lane * 8;
+    const XT *uval = static_cast<const XT *>(p.uval);
+    const uint32_t hw = nvalid > 0 ? __ldg(p.headw + (q >> 5)) : 0u;
+    L.hb = (hw >> ((lane & 3) * 8)) & 0xffu;                               // this lane's 8 row-start bits
+    L.rank = __ldg(p.run_base + run) + __ldg(p.lane_rank + run * 32 + lane);   // row starts before this lane's first entry
+    L.nvalid = nvalid;
+    if (SPARSE) {
+        // u has holes: a product exists only where u(col) does; the values are fetched only for those
+#pragma unroll
+        for (int j = 0; j < 8; ++j) L.up[j] = j < nvalid ? __ldg(p.upres + c[j]) : (uint8_t)0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) L.uv[j] = (NEED_U && L.up[j]) ? gload<XT>(uval + c[j]) : (XT)0;
+    } else if (NEED_U) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) L.uv[j] = gather(c[j]);
+    }
+}
+
+// Part 2: multiply, fold between the row-start bits, segmented scan over the lanes, stores.
+template <typename XT, typename ZT, int ADD_C, int MUL_C, bool SPARSE>
+__device__ __forceinline__ void spmv_run_fold(const RunArgs &p, const int64_t run, const int lane, const RunLane<XT> &L) {
     // ADD_C / MUL_C >= 0: compile-time semiring; -1: run-time operator codes (both operands are read)
     constexpr bool NEED_A = MUL_C < 0 || mul_reads_x(MUL_C);
     constexpr bool NEED_U = MUL_C < 0 || mul_reads_y(MUL_C);
     const int ADD = ADD_C >= 0 ? ADD_C : p.add_op;
     const int MUL = MUL_C >= 0 ? MUL_C : p.mul_op;
-    const int64_t q = run * RUN + lane * 8;
-    const XT *uval = static_cast<const XT *>(p.uval);
     ZT *tval = static_cast<ZT *>(p.tval);
-    const uint32_t hw = nvalid > 0 ? __ldg(p.headw + (q >> 5)) : 0u;
-    const uint32_t hb = (hw >> ((lane & 3) * 8)) & 0xffu;                 // this lane's 8 row-start bits
-    uint32_t rank = __ldg(p.run_base + run) + __ldg(p.lane_rank + run * 32 + lane);   // row starts before this lane's first entry
-    XT uv[8]; uint8_t up[8];
-    if (SPARSE) {
-        // u has holes: a product exists only where u(col) does; the values are fetched only for those
-#pragma unroll
-        for (int j = 0; j < 8; ++j) up[j] = j < nvalid ? __ldg(p.upres + c[j]) : (uint8_t)0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) uv[j] = (NEED_U && up[j]) ? gload<XT>(uval + c[j]) : (XT)0;
-    } else if (NEED_U) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) uv[j] = gather(c[j]);
-    }
+    const int nvalid = L.nvalid;
+    const uint32_t hb = L.hb; uint32_t rank = L.rank;
+    const uint8_t (&up)[8] = L.up;
     ZT prod[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const XT av = NEED_A ? a[j] : (XT)1, uu = NEED_U ? uv[j] : (XT)1;
+        const XT av = NEED_A ? L.a[j] : (XT)1, uu = NEED_U ? L.uv[j] : (XT)1;
         prod[j] = (MUL_C < 0 && p.flip) ? MulApply<XT, ZT>::f(MUL, uu, av) : MulApply<XT, ZT>::f(MUL, av, uu);
     }
 
@@ -131,10 +144,11 @@ __global__ void __launch_bounds__(256) spmv_run_kernel(const RunArgs p) {
     const int64_t run = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (run >= p.nruns) return;
     const int lane = threadIdx.x & 31;
-    uint32_t c[8]; XT a[8];
-    const int nvalid = spmv_run_load_global<XT, ZT, MUL>(p, run, lane, c, a);
+    uint32_t c[8]; RunLane<XT> L;
+    const int nvalid = spmv_run_load_global<XT, ZT, MUL>(p, run, lane, c, L.a);
     const XT *uval = static_cast<const XT *>(p.uval);
-    spmv_run_finish<XT, ZT, ADD, MUL, SPARSE>(p, run, lane, nvalid, c, a, [uval](uint32_t col) { return gload<XT>(uval + col); });
+    spmv_run_gather<XT, MUL, SPARSE>(p, run, lane, nvalid, c, L, [uval](uint32_t col) { return gload<XT>(uval + col); });
+    spmv_run_fold<XT, ZT, ADD, MUL, SPARSE>(p, run, lane, L);
 }
 
 // ==================================================================================================
@@ -220,36 +234,52 @@ __global__ void __launch_bounds__(HOT2_WARPS * 32, 1) spmv_run_hot2_kernel(const
         if (col < henc) return gload<XT>(uhot + col);
         return gload<XT>(uval + (col - henc));
     };
+    // Software pipeline over the warp's runs: the words of run r+1 are copied out of the stage and its gathers of u
+    // are ISSUED before run r is multiplied, folded and stored, so the gather latency sits under a run's worth of
+    // arithmetic instead of in front of it (and the bulk copy of run r+2 is in flight under both).
     uint32_t parity = 0;
-    for (; run < p.nruns; run += stride) {
+    RunLane<XT> cur, nxt;
+    int64_t cur_run = -1;
+    auto fetch = [&](int64_t r, RunLane<XT> &L) {
         mbar_wait(bar, parity); parity ^= 1u;
-        const int64_t q = run * RUN + lane * 8;
+        const int64_t q = r * RUN + lane * 8;
         const int nvalid = (int)min((int64_t)8, max((int64_t)0, p.nnz - q));
-        uint32_t c[8]; XT a[8];
-        {
-            const uint4 *sc = reinterpret_cast<const uint4 *>(stage) + lane * 2;
-            const uint4 c0 = sc[0], c1 = sc[1];
-            c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
-            if (NEED_A) {
-                const XT *sa = reinterpret_cast<const XT *>(stage + RUN * 4) + lane * 8;
-                if constexpr (sizeof(XT) == 4) {
-                    const uint4 a0 = reinterpret_cast<const uint4 *>(sa)[0], a1 = reinterpret_cast<const uint4 *>(sa)[1];
-                    const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        uint32_t c[8];
+        const uint4 *sc = reinterpret_cast<const uint4 *>(stage) + lane * 2;
+        const uint4 c0 = sc[0], c1 = sc[1];
+        c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+        if (NEED_A) {
+            const XT *sa = reinterpret_cast<const XT *>(stage + RUN * 4) + lane * 8;
+            if constexpr (sizeof(XT) == 4) {
+                const uint4 a0 = reinterpret_cast<const uint4 *>(sa)[0], a1 = reinterpret_cast<const uint4 *>(sa)[1];
+                const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) a[j] = reinterpret_cast<const XT &>(w[j]);
-                } else {
+                for (int j = 0; j < 8; ++j) L.a[j] = reinterpret_cast<const XT &>(w[j]);
+            } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) a[j] = sa[j];
-                }
-            }
-            if (nvalid < 8) {                                                   // tail of the last run: what lies past nnz is not data
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { if (j >= nvalid) { c[j] = henc; if (NEED_A) a[j] = (XT)1; } }
+                for (int j = 0; j < 8; ++j) L.a[j] = sa[j];
             }
         }
-        __syncwarp();                                                           // every lane has its words: the stage is free
-        if (lane == 0 && run + stride < p.nruns) issue(run + stride);
-        spmv_run_finish<XT, ZT, ADD, MUL, false>(p, run, lane, nvalid, c, a, gather);
+        if (nvalid < 8) {                                                   // tail of the last run: what lies past nnz is not data
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { if (j >= nvalid) { c[j] = henc; if (NEED_A) L.a[j] = (XT)1; } }
+        }
+        __syncwarp();                                                       // every lane has its words: the stage is free
+        if (lane == 0 && r + stride < p.nruns) issue(r + stride);
+        spmv_run_gather<XT, MUL, false>(p, r, lane, nvalid, c, L, gather);
+    };
+    if constexpr (sizeof(XT) > 4) {
+        // 8-byte values: two runs in flight do not fit in 64 registers per thread -- one at a time
+        for (; run < p.nruns; run += stride) { fetch(run, cur); spmv_run_fold<XT, ZT, ADD, MUL, false>(p, run, lane, cur); }
+        (void)nxt; (void)cur_run;
+    } else {
+        if (run < p.nruns) { fetch(run, cur); cur_run = run; run += stride; }
+        while (cur_run >= 0) {
+            const bool more = run < p.nruns;
+            if (more) fetch(run, nxt);
+            spmv_run_fold<XT, ZT, ADD, MUL, false>(p, cur_run, lane, cur);
+            if (more) { cur = nxt; cur_run = run; run += stride; } else cur_run = -1;
+        }
     }
 }
 

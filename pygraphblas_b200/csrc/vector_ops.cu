@@ -125,6 +125,16 @@ GrB_Info vector_write(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp ac
     std::string *err = &w->err;
     const int64_t n = (int64_t)w->n;
     const int wtc = w->type->code;
+    if (!mask && f.mask_comp) {
+        // w<!NULL>: the complement of "no mask" lets nothing through -- w keeps its entries, or loses all of
+        // them under GrB_REPLACE (GraphBLAS C API 1.3 section 4.3; SuiteSparse's quick-mask exit)
+        if (own_t) { dfree(tval); dfree(tpres); }
+        if (f.replace) {
+            vector_invalidate_device(w);
+            w->hi.clear(); w->hx.clear(); w->pi.clear(); w->px.clear(); w->host_valid = true;
+        }
+        return GrB_SUCCESS;
+    }
     const bool need_final = mask != nullptr || accum != nullptr || region != nullptr || t_scalar || !own_t;
     if (!need_final) {
         if (wtc == ttc) vector_adopt_device(w, tval, tpres);
@@ -303,7 +313,7 @@ static GrB_Info vec_bind(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
 // ------------------------------------------------------------------ index lists (GrB_ALL, explicit, GxB_RANGE / STRIDE / BACKWARDS)
 extern "C" const GrB_Index *GrB_ALL;
 // Expands (I, ni) over a dimension of `dim` positions.  all = true: every position in order (no list needed).
-static GrB_Info index_list(const GrB_Index *I, GrB_Index ni, uint64_t dim, bool *all, std::vector<uint64_t> &out, std::string *err, const char *fn) {
+GrB_Info index_list(const GrB_Index *I, GrB_Index ni, uint64_t dim, bool *all, std::vector<uint64_t> &out, std::string *err, const char *fn) {
     *all = false; out.clear();
     if (!I) return gb_fail(GrB_NULL_POINTER, err, "%s: NULL index list", fn);
     if (I == GrB_ALL) { *all = true; return GrB_SUCCESS; }

@@ -81,3 +81,82 @@ def allgather_slices(full, local, bounds):
     for w in dist.batch_isend_irecv(ops) if ops else []:
         w.wait()
     return full
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The exchange step inside the library (csrc/dist.cu): peers write each other's HBM over NVLink with the library's
+# own kernels; this module only carries the 64-byte CUDA-IPC handles between the processes (control plane).
+def equal_row_blocks(n, world, align=16):
+    """Row offsets of `world` contiguous blocks of (almost) equal length, every block starting at a multiple of
+    `align` rows (the library moves slices as 16-byte words)."""
+    per = -(-n // world)
+    per = -(-per // align) * align
+    return [min(n, r * per) for r in range(world + 1)]
+
+
+def exchange_handles(handle, world, rank, gather=None):
+    """All ranks' 64-byte handles, in rank order, as one bytes object.  `gather(list_out, obj)` defaults to
+    torch.distributed.all_gather_object (works on gloo and nccl process groups alike)."""
+    if world == 1:
+        return bytes(handle)
+    if gather is None:
+        import torch.distributed as dist
+        gather = dist.all_gather_object
+    out = [None] * world
+    gather(out, bytes(handle))
+    assert all(isinstance(h, (bytes, bytearray)) and len(h) == 64 for h in out), "IPC handles are 64 bytes"
+    return b"".join(bytes(h) for h in out)
+
+
+class Comm:
+    """A communicator for replicated vectors of length n (B200_Comm_* of include/b200grb.h).
+
+        comm = Comm(n, FP32)                         # collective: every rank of the process group
+        w_slice = A_local.mxv(u, semiring=...)       # local rows
+        w = comm.allgather(w_slice, row0)            # Vector view of the replicated result (borrowed)
+        p = comm.allreduce(partial, FP32.PLUS_MONOID)
+    """
+
+    def __init__(self, n, typ, rank=None, world=None, gather=None):
+        from .base import lib, ffi, _check
+        from .vector import Vector
+        if rank is None or world is None:
+            import torch.distributed as dist
+            rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+        self._lib, self._ffi, self._check, self._Vector = lib, ffi, _check, Vector
+        self.rank, self.world, self.n, self.type = rank, world, n, typ
+        self._comm = ffi.new("B200_Comm*")
+        _check(lib.B200_Comm_create(self._comm, rank, world, n, typ.gb_type))
+        h = ffi.new("unsigned char[64]")
+        _check(lib.B200_Comm_handle(self._comm[0], h))
+        allh = exchange_handles(bytes(ffi.buffer(h, 64)), world, rank, gather)
+        _check(lib.B200_Comm_connect(self._comm[0], ffi.from_buffer(allh)))
+        self.bounds = equal_row_blocks(n, world)
+
+    def _view(self):
+        v = self._ffi.new("GrB_Vector*")
+        self._check(self._lib.B200_Comm_result(self._comm[0], v))
+        return self._Vector(v, owner=self)      # the communicator owns the handle: never freed through the view
+
+    def allgather(self, slice_vec, row0=None):
+        row0 = self.bounds[self.rank] if row0 is None else row0
+        self._check(self._lib.B200_Comm_allgather(self._comm[0], slice_vec._vector[0], row0))
+        return self._view()
+
+    def allreduce(self, partial, monoid):
+        self._check(self._lib.B200_Comm_allreduce(self._comm[0], partial._vector[0], getattr(monoid, "monoid", monoid)))
+        return self._view()
+
+    def barrier(self):
+        self._check(self._lib.B200_Comm_barrier(self._comm[0]))
+
+    def close(self):
+        if self._comm is not None:
+            self._lib.B200_Comm_free(self._comm)
+            self._comm = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

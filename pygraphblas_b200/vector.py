@@ -14,14 +14,15 @@ GxB_INDEX_MAX = 1 << 60
 
 
 class Vector:
-    __slots__ = ("_vector", "_mask_alive", "_keep_scalar", "__weakref__")
+    __slots__ = ("_vector", "_mask_alive", "_keep_scalar", "_owner", "__weakref__")
 
-    def __init__(self, handle):
+    def __init__(self, handle, owner=None):
         self._vector = handle
+        self._owner = owner          # set for views whose handle belongs to another object (distributed.Comm): not freed here
 
     def __del__(self):
         try:        # at interpreter shutdown the binding may already be torn down
-            if lib is not None and getattr(self, "_vector", None) is not None:
+            if lib is not None and getattr(self, "_vector", None) is not None and getattr(self, "_owner", None) is None:
                 lib.GrB_Vector_free(self._vector)
         except Exception:
             pass

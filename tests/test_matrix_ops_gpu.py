@@ -194,3 +194,75 @@ def test_triangle_count_end_to_end():
     Ak = Matrix.from_scipy(sp.csr_matrix(K), INT64)
     Lk = Ak.tril(-1)
     assert Lk.mxm(Lk, mask=Lk, semiring=INT64.PLUS_PAIR).reduce_int() == 45          # demo/Triangle-Counting.ipynb:33,56
+
+
+# ------------------------------------------------------------------ GrB_Matrix_assign_<T> (matrix_assign.cu)
+def _mdict(m):
+    I, J, X = m.to_arrays()
+    return {(int(i), int(j)): int(x) for i, j, x in zip(I, J, X)}
+
+
+def _assign_scalar_model(C, M, accum, x, I, J, mask_struct, mask_comp, replace):
+    """GrB_assign of a scalar, C API 1.3 section 4.3.7.6, on dicts: Z = C with the region I x J set to x (or accum(C, x));
+    then the mask -- which spans all of C -- and GrB_REPLACE."""
+    Z = dict(C)
+    for k in itertools.product(I, J):
+        Z[k] = (C[k] + x) if (accum and k in C) else x
+    out = {}
+    for k in set(C) | set(Z):
+        if M is None:
+            m = not mask_comp
+        else:
+            m = k in M and (mask_struct or M[k] != 0)
+            m = (not m) if mask_comp else m
+        if m:
+            if k in Z:
+                out[k] = Z[k]
+        elif not replace and k in C:
+            out[k] = C[k]
+    return out
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_matrix_assign_scalar_against_model(seed):
+    """C<M>(I,J) = accum(C(I,J), x) through the C ABI, over GrB_ALL / explicit lists / GxB_RANGE / GxB_STRIDE index forms,
+    value / structural / complemented masks, GrB_REPLACE and a PLUS accumulator."""
+    rng = np.random.default_rng(300 + seed)
+    nr, nc = int(rng.integers(3, 14)), int(rng.integers(3, 14))
+    def rand(dens):
+        k = int(round(nr * nc * dens))
+        flat = rng.choice(nr * nc, size=k, replace=False)
+        return Matrix.from_lists(flat // nc, flat % nc, rng.integers(-3, 4, k), nr, nc, INT64)
+    C = rand([0.0, 0.3, 0.6][seed % 3])
+    M = rand(0.5) if seed % 2 else None
+    dname = ["", "S", "C", "R", "RC", "RSC"][seed % 6]
+    desc = getattr(descriptor, dname) if dname else None
+    accum = INT64.PLUS if seed % 4 >= 2 else None
+    ffi = gb.ffi
+    form = seed % 4
+    if form == 0:
+        I, Iarg, ni = list(range(nr)), lib.GrB_ALL, 0
+    elif form == 1:
+        I = sorted(set(rng.integers(0, nr, 3).tolist())); Iarg = ffi.new("GrB_Index[]", I); ni = len(I)
+    elif form == 2:
+        lo, hi = sorted(rng.integers(0, nr, 2).tolist()); I = list(range(lo, hi + 1)); Iarg = ffi.new("GrB_Index[]", [lo, hi]); ni = lib.GxB_RANGE
+    else:
+        lo, hi = 0, nr - 1; I = list(range(lo, hi + 1, 2)); Iarg = ffi.new("GrB_Index[]", [lo, hi, 2]); ni = lib.GxB_STRIDE
+    if seed % 3 == 0:
+        J, Jarg, nj = list(range(nc)), lib.GrB_ALL, 0
+    else:
+        J = rng.integers(0, nc, 4).tolist(); Jarg = ffi.new("GrB_Index[]", J); nj = len(J)      # duplicates allowed
+    expect = _assign_scalar_model(_mdict(C), _mdict(M) if M else None, accum is not None, 7, I, sorted(set(J)),
+                                  "S" in dname, "C" in dname, "R" in dname)
+    info = lib.GrB_Matrix_assign_INT64(C._matrix[0], M._matrix[0] if M else ffi.NULL, accum.get_op() if accum else ffi.NULL, 7,
+                                       Iarg, ni, Jarg, nj, desc.get_desc() if desc else ffi.NULL)
+    assert info == 0, ffi.string(lib.B200_last_error())
+    assert _mdict(C) == expect, (seed, dname, form)
+
+
+def test_dense_fill_like_the_reference_test_pow():
+    """Matrix.dense (/root/reference/pygraphblas/matrix.py:183 -> assign_scalar :179) as tests/test_matrix.py:858-864 uses it."""
+    m = Matrix.sparse(gb.UINT8, 10, 10)
+    assert lib.GrB_Matrix_assign_UINT8(m._matrix[0], gb.ffi.NULL, gb.ffi.NULL, 1, lib.GrB_ALL, 0, lib.GrB_ALL, 0, gb.ffi.NULL) == 0
+    assert m.nvals == 100 and set(m.to_arrays()[2].tolist()) == {1}
+    assert (m @ m).iseq(m ** 2) and set((m ** 3).to_arrays()[2].tolist()) == {100}

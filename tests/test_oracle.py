@@ -52,6 +52,19 @@ def test_oracle_matches_python_model(seed):
         assert got[kk] == expect[kk].item(), (seed, sr, desc, kk, got[kk], expect[kk])
 
 
+@pytest.mark.parametrize("desc", ["C", "RC", "SC", "RSC"])
+def test_oracle_complemented_null_mask(desc):
+    """C<!NULL>: nothing is let through; REPLACE clears C (both restatements agree, C API 1.3 section 4.3)."""
+    rng = np.random.default_rng(5)
+    A, B, C = util.rand_mat(rng, "INT32", 6, 6, 0.5), util.rand_mat(rng, "INT32", 6, 6, 0.5), util.rand_mat(rng, "INT32", 6, 6, 0.4)
+    sr = ("PLUS", "TIMES", "INT32")
+    for accum in (None, ("PLUS", "INT32")):
+        got = orc.mxm(util.o_mat(C), None, accum, sr, util.o_mat(A), util.o_mat(B), desc).todict()
+        expect = pymodel.mxm(_dict(C), "INT32", None, None, accum, sr, _dict(A), "INT32", _dict(B), "INT32", orc.parse_desc(desc))
+        assert set(got) == set(expect) == (set() if "R" in desc else set(_dict(C)))
+        assert all(got[k] == _dict(C)[k] for k in got)
+
+
 def test_oracle_plus_times_matches_scipy():
     # BASELINE.json configs[0]: 1024 x 1024 random 1% CSR, PLUS_TIMES_FP64 mxv
     A = sp.random(1024, 1024, density=0.01, format="csr", dtype=np.float64, random_state=0)

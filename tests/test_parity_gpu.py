@@ -114,6 +114,27 @@ def test_random_mxv_vxm_against_oracle(seed):
     _check(case, util.product_run(case))
 
 
+@pytest.mark.parametrize("op", ["mxv", "vxm", "mxm"])
+@pytest.mark.parametrize("desc", ["C", "RC", "SC", "RSC"])
+@pytest.mark.parametrize("acc", [None, "PLUS"])
+def test_complemented_null_mask(op, desc, acc):
+    """C<!NULL> / w<!NULL>: the complement of "no mask" lets nothing through -- the output keeps its entries, or is
+    cleared under GrB_REPLACE (C API 1.3 section 4.3; SuiteSparse's quick-mask exit), for every entry point."""
+    rng = np.random.default_rng(77)
+    A = util.rand_mat(rng, "INT64", 9, 9, 0.4)
+    accum = (acc, "INT64") if acc else None
+    if op == "mxm":
+        case = {"op": "mxm", "A": A, "B": util.rand_mat(rng, "INT64", 9, 9, 0.4), "C": util.rand_mat(rng, "INT64", 9, 9, 0.3),
+                "mask": None, "accum": accum, "semiring": ["PLUS", "TIMES", "INT64"], "desc": desc}
+    else:
+        case = {"op": op, "A": A, "u": util.rand_vec(rng, "INT64", 9, 0.7), "w": util.rand_vec(rng, "INT64", 9, 0.5),
+                "mask": None, "accum": accum, "semiring": ["PLUS", "TIMES", "INT64"], "desc": desc}
+    got = util.product_run(case)
+    _check(case, got)
+    before = case["C"] if op == "mxm" else case["w"]
+    assert len(got.I) == (0 if "R" in desc else len(before["I"]))
+
+
 @pytest.mark.parametrize("seed", range(120))
 def test_random_mxm_against_oracle(seed):
     rng = np.random.default_rng(5000 + seed)

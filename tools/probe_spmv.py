@@ -37,6 +37,14 @@ def run(label, sr, env):
     ms = e0.elapsed_time(e1) / 30
     print(f"{label:44s} {ms*1e3:8.1f} us", flush=True)
 
+if len(sys.argv) > 2 and sys.argv[2] == "sweep":
+    run("default PLUS_TIMES", FP32.PLUS_TIMES, {})
+    for kb in ("0", "16", "32", "48", "64", "80", "96", "100", "112", "120", "128", "130", "136", "144", "160"):
+        run(f"hot table cap {kb}KB PLUS_TIMES", FP32.PLUS_TIMES, {"B200GRB_SPMV_HOT": kb})
+    run("default MIN_PLUS", FP32.MIN_PLUS, {})
+    run("default PLUS_SECOND", FP32.PLUS_SECOND, {})
+    run("PLUS_FIRST (no gather)", FP32.PLUS_FIRST, {})
+    sys.exit(0)
 run("default (hot table, TMA staged) PLUS_TIMES", FP32.PLUS_TIMES, {})
 run("run kernel PLUS_SECOND", FP32.PLUS_SECOND, {})
 run("run kernel PLUS_FIRST (no gather)", FP32.PLUS_FIRST, {})
