@@ -195,7 +195,9 @@ GrB_Info GrB_vxm(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, 
  * Bulk ingest / egress (the reference has none: Matrix.from_lists loops
  * setElement, /root/reference/pygraphblas/matrix.py:325-330) and device interop.
  * `where`: 0 = the pointers are host memory, 1 = CUDA device memory of the
- * current device (e.g. a torch tensor's data_ptr()).                            */
+ * current device (e.g. a torch tensor's data_ptr()), 2 (vector set / export only) = PINNED host
+ * memory copied on the library's copy streams, overlapping kernels already enqueued: GraphBLAS
+ * non-blocking mode -- an export's data is in host memory after GrB_Vector_wait / B200_device_synchronize. */
 GrB_Info B200_Matrix_import_CSR(GrB_Matrix *A, GrB_Type type, GrB_Index nrows, GrB_Index ncols,
                                 const int64_t *Ap, const uint32_t *Aj, const void *Ax,
                                 GrB_Index nvals, int where);

@@ -115,6 +115,9 @@ struct GB_Vector_opaque {
     // device form: dense values + presence bytes (present == nullptr: all present)
     void *dval = nullptr; uint8_t *dpres = nullptr; bool dev_valid = false; int64_t dev_nvals = -1;
     bool borrowed = false;     // dval / dpres belong to a communicator (dist.cu): never freed through the vector
+    // overlapped host copies (B200_Vector_set_dense / export_dense with where = 2): the copy streams' hand-shakes with the compute stream
+    cudaEvent_t ev_h2d = nullptr, ev_d2h = nullptr, ev_use = nullptr;
+    bool h2d_pending = false, d2h_pending = false, use_recorded = false;
     std::string err;
 };
 
@@ -125,6 +128,7 @@ struct GBGlobal {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t h2d = nullptr, d2h = nullptr;     // copy streams of the overlapped import / export (where = 2)
     uint64_t launches = 0;
     uint64_t last_flops = 0, last_nnz_out = 0;
     int burble = 0;
@@ -156,6 +160,7 @@ struct Tunables {
     int spmv_run = -1;         // B200GRB_SPMV_RUN     -1 default choice, 0 never, 1 always the run kernel
     int spmv_hot_kb = -1;      // B200GRB_SPMV_HOT     -1 default (on when the gathers are concentrated), 0 off, >0 table cap in KB
     bool no_pull = false, no_push = false, force_push = false, spmv_debug = false;
+    bool spmv_pipe = false;    // B200GRB_SPMV_PIPE    software-pipeline two runs per warp in the hot-table kernel (4-byte types)
     int spgemm_v = 0;          // B200GRB_SPGEMM_V     masked SpGEMM kernel generation (0 = default)
 };
 const Tunables &tunables();
@@ -189,6 +194,7 @@ GrB_Info vector_ensure_host(GrB_Vector v);
 GrB_Info vector_ensure_device(GrB_Vector v);
 void vector_invalidate_device(GrB_Vector v);
 void vector_adopt_device(GrB_Vector v, void *vals, uint8_t *pres);
+void vector_mark_used(GrB_Vector v);               // after the kernels reading v were enqueued (lets the next overlapped import of v start early)
 bool gb_valid_matrix(const GrB_Matrix A);
 bool gb_valid_vector(const GrB_Vector v);
 

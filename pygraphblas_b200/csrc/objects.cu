@@ -42,6 +42,7 @@ static void tunables_load() {
     t.spmv_hot_kb = geti("B200GRB_SPMV_HOT", -1);
     t.no_pull = getenv("B200GRB_NO_PULL") != nullptr; t.no_push = getenv("B200GRB_NO_PUSH") != nullptr;
     t.force_push = getenv("B200GRB_FORCE_PUSH") != nullptr; t.spmv_debug = getenv("B200GRB_SPMV_DEBUG") != nullptr;
+    t.spmv_pipe = geti("B200GRB_SPMV_PIPE", 0) != 0;
     t.spgemm_v = geti("B200GRB_SPGEMM_V", 0);
     g_tun = t; g_tun_loaded = true;
 }
@@ -157,6 +158,7 @@ extern "C" GrB_Info B200_device_synchronize(void) {
     GB_LOCK;
     if (!G.have_device) return GrB_SUCCESS;
     CU_TRY(cudaStreamSynchronize(G.stream), nullptr);
+    if (G.h2d) { CU_TRY(cudaStreamSynchronize(G.h2d), nullptr); CU_TRY(cudaStreamSynchronize(G.d2h), nullptr); }
     return GrB_SUCCESS;
 }
 
@@ -399,7 +401,16 @@ bool gb_valid_vector(const GrB_Vector v) { return v && v->magic == GB_MAGIC; }
 static const uint64_t DEV_DIM_MAX = ((uint64_t)1 << 31) - 1;   // 32-bit column / row ids in HBM
 
 void matrix_invalidate_device(GrB_Matrix A) { csr_free(A->dev); csr_free(A->devT); }
+// copies still running on the copy streams must finish before the compute stream frees (or overwrites) the buffers
+static void vector_join_copies(GrB_Vector v) {
+    if (v->h2d_pending) { cudaStreamWaitEvent(G.stream, v->ev_h2d, 0); v->h2d_pending = false; }
+    if (v->d2h_pending) { cudaStreamWaitEvent(G.stream, v->ev_d2h, 0); v->d2h_pending = false; }
+}
+void vector_mark_used(GrB_Vector v) {
+    if (v && v->ev_use) { cudaEventRecord(v->ev_use, G.stream); v->use_recorded = true; }
+}
 void vector_invalidate_device(GrB_Vector v) {
+    vector_join_copies(v);
     if (!v->borrowed) { dfree(v->dval); dfree(v->dpres); }       // a borrowed view (B200_Comm_result) does not own its buffers
     v->borrowed = false; v->dval = nullptr; v->dpres = nullptr; v->dev_valid = false; v->dev_nvals = -1;
 }
@@ -558,6 +569,7 @@ __global__ void vec_scatter_kernel(const uint64_t *idx, const uint8_t *x, uint8_
 GrB_Info vector_ensure_device(GrB_Vector v) {
     if (!G.have_device) return gb_fail(GrB_PANIC, &v->err, "no CUDA device: libb200grb computes only on the GPU (no CPU fallback)");
     if (v->host_valid) GB_TRY(vector_flush_pending(v));
+    if (v->h2d_pending) { cudaStreamWaitEvent(G.stream, v->ev_h2d, 0); v->h2d_pending = false; }     // an overlapped import is in flight
     if (v->dev_valid) return GrB_SUCCESS;
     if (v->n > DEV_DIM_MAX) return gb_fail(GrB_INVALID_VALUE, &v->err, "vector size %llu exceeds the 2^31-1 limit of the HBM layout", (unsigned long long)v->n);
     const size_t sz = v->type->size, n = (size_t)v->n, k = v->hi.size();
@@ -804,7 +816,11 @@ extern "C" GrB_Info GrB_Vector_new(GrB_Vector *v, GrB_Type type, GrB_Index n) {
 extern "C" GrB_Info GrB_Vector_free(GrB_Vector *v) {
     GB_LOCK;
     if (!v || !*v) return GrB_SUCCESS;
-    if ((*v)->magic == GB_MAGIC) { vector_invalidate_device(*v); (*v)->magic = GB_FREED; delete *v; }
+    if ((*v)->magic == GB_MAGIC) {
+        vector_invalidate_device(*v);
+        if ((*v)->ev_h2d) { cudaEventDestroy((*v)->ev_h2d); cudaEventDestroy((*v)->ev_d2h); cudaEventDestroy((*v)->ev_use); }
+        (*v)->magic = GB_FREED; delete *v;
+    }
     *v = nullptr; return GrB_SUCCESS;
 }
 extern "C" GrB_Info GrB_Vector_dup(GrB_Vector *w, const GrB_Vector u) {
@@ -856,7 +872,17 @@ extern "C" GrB_Info GrB_Vector_wait(GrB_Vector *v) {
     GB_LOCK;
     if (!v) return gb_fail(GrB_NULL_POINTER, nullptr, "GrB_Vector_wait: NULL"); GB_VECTOR_OK(*v, "GrB_Vector_wait");
     if ((*v)->host_valid) GB_TRY(vector_flush_pending(*v));
-    if (G.have_device) CU_TRY(cudaStreamSynchronize(G.stream), &(*v)->err);
+    if (G.have_device) {
+        if ((*v)->d2h_pending) {
+            // an overlapped export of v is in flight: its completion implies that of every kernel that produced v, and it is all this
+            // vector is waiting for -- the compute stream itself (later, unrelated steps) is left running
+            CU_TRY(cudaEventSynchronize((*v)->ev_d2h), &(*v)->err);
+            (*v)->d2h_pending = false;
+        } else {
+            CU_TRY(cudaStreamSynchronize(G.stream), &(*v)->err);
+            if ((*v)->h2d_pending) { CU_TRY(cudaEventSynchronize((*v)->ev_h2d), &(*v)->err); (*v)->h2d_pending = false; }
+        }
+    }
     return GrB_SUCCESS;
 }
 extern "C" GrB_Info GrB_Vector_error(const char **error, const GrB_Vector v) {
@@ -980,6 +1006,19 @@ extern "C" GrB_Info GxB_Vector_fprint(GrB_Vector v, const char *name, int pr, FI
 }
 
 // ------------------------------------------------------------------ bulk import / export (B200 extensions)
+// first overlapped copy of a vector: the copy streams and the vector's events
+static GrB_Info vector_async_setup(GrB_Vector v) {
+    if (!G.h2d) {
+        CU_TRY(cudaStreamCreateWithFlags(&G.h2d, cudaStreamNonBlocking), &v->err);
+        CU_TRY(cudaStreamCreateWithFlags(&G.d2h, cudaStreamNonBlocking), &v->err);
+    }
+    if (!v->ev_h2d) {
+        CU_TRY(cudaEventCreateWithFlags(&v->ev_h2d, cudaEventDisableTiming), &v->err);
+        CU_TRY(cudaEventCreateWithFlags(&v->ev_d2h, cudaEventDisableTiming), &v->err);
+        CU_TRY(cudaEventCreateWithFlags(&v->ev_use, cudaEventDisableTiming), &v->err);
+    }
+    return GrB_SUCCESS;
+}
 static GrB_Info copy_in(void *dst, const void *src, size_t bytes, int where, std::string *err) {
     if (!bytes) return GrB_SUCCESS;
     CU_TRY(cudaMemcpyAsync(dst, src, bytes, where ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, G.stream), err);
@@ -1040,11 +1079,28 @@ extern "C" GrB_Info B200_Vector_set_dense(GrB_Vector v, const void *x, const uin
     if (!G.have_device) return gb_fail(GrB_PANIC, &v->err, "no CUDA device: libb200grb computes only on the GPU (no CPU fallback)");
     if (v->n > DEV_DIM_MAX) return gb_fail(GrB_INVALID_VALUE, &v->err, "vector size exceeds 2^31-1");
     const size_t sz = v->type->size, n = (size_t)v->n;
+    if (where == 2) GB_TRY(vector_async_setup(v));
+    const bool fresh = !v->dev_valid || !v->dval || (present && !v->dpres) || (!present && v->dpres);
     if (!v->dev_valid || !v->dval) { vector_invalidate_device(v); GB_TRY(dmalloc(&v->dval, n * sz + 16, &v->err)); }
     if (present && !v->dpres) GB_TRY(dmalloc((void **)&v->dpres, n + 16, &v->err));
-    if (!present && v->dpres) { dfree(v->dpres); v->dpres = nullptr; }
-    GB_TRY(copy_in(v->dval, x, n * sz, where, &v->err));
-    if (present) GB_TRY(copy_in(v->dpres, present, n, where, &v->err));
+    if (!present && v->dpres) { vector_join_copies(v); dfree(v->dpres); v->dpres = nullptr; }
+    if (where == 2) {
+        // pinned host memory, copied on the import stream so that it overlaps kernels already enqueued on the compute stream.
+        // The copy may start once the last kernels that READ this vector are done (their event, recorded by the call that
+        // used it) -- or, when the buffers are new or the use was not recorded, once everything enqueued so far is done.
+        if (v->use_recorded && !fresh) cudaStreamWaitEvent(G.h2d, v->ev_use, 0);
+        else { cudaEventRecord(v->ev_use, G.stream); cudaStreamWaitEvent(G.h2d, v->ev_use, 0); }
+        v->use_recorded = false;
+        if (v->d2h_pending) cudaStreamWaitEvent(G.h2d, v->ev_d2h, 0);
+        CU_TRY(cudaMemcpyAsync(v->dval, x, n * sz, cudaMemcpyHostToDevice, G.h2d), &v->err);
+        if (present) CU_TRY(cudaMemcpyAsync(v->dpres, present, n, cudaMemcpyHostToDevice, G.h2d), &v->err);
+        CU_TRY(cudaEventRecord(v->ev_h2d, G.h2d), &v->err);
+        v->h2d_pending = true;
+    } else {
+        vector_join_copies(v);
+        GB_TRY(copy_in(v->dval, x, n * sz, where, &v->err));
+        if (present) GB_TRY(copy_in(v->dpres, present, n, where, &v->err));
+    }
     v->dev_valid = true; v->dev_nvals = present ? -1 : (int64_t)n;
     v->hi.clear(); v->hx.clear(); v->pi.clear(); v->px.clear(); v->host_valid = false;
     return GrB_SUCCESS;
@@ -1061,6 +1117,22 @@ extern "C" GrB_Info B200_Vector_export_dense(const GrB_Vector v, void *x, uint8_
     GB_LOCK; GB_VECTOR_OK(v, "B200_Vector_export_dense");
     GB_TRY(vector_ensure_device(v));
     const size_t sz = v->type->size, n = (size_t)v->n;
+    if (where == 2) {
+        // pinned host memory, copied on the export stream once everything enqueued so far on the compute stream is done; the data
+        // is in host memory after GrB_Vector_wait(v) / B200_device_synchronize (GraphBLAS non-blocking mode)
+        GB_TRY(vector_async_setup(v));
+        if (v->d2h_pending) cudaStreamWaitEvent(G.d2h, v->ev_d2h, 0);
+        CU_TRY(cudaEventRecord(v->ev_d2h, G.stream), &v->err);
+        CU_TRY(cudaStreamWaitEvent(G.d2h, v->ev_d2h, 0), &v->err);
+        if (x) CU_TRY(cudaMemcpyAsync(x, v->dval, n * sz, cudaMemcpyDeviceToHost, G.d2h), &v->err);
+        if (present) {
+            if (v->dpres) CU_TRY(cudaMemcpyAsync(present, v->dpres, n, cudaMemcpyDeviceToHost, G.d2h), &v->err);
+            else memset(present, 1, n);
+        }
+        CU_TRY(cudaEventRecord(v->ev_d2h, G.d2h), &v->err);
+        v->d2h_pending = true;
+        return GrB_SUCCESS;
+    }
     if (x) GB_TRY(copy_out(x, v->dval, n * sz, where, &v->err));
     if (present) {
         if (v->dpres) GB_TRY(copy_out(present, v->dpres, n, where, &v->err));

@@ -765,6 +765,8 @@ template <bool FILL> __global__ void mat_finalize_kernel(const MatFinalizeArgs a
     }
 }
 
+#include "spgemm_stream.cuh"
+
 // ------------------------------------------------------------------ host side
 struct TypedCsr { Csr c; int tc; };   // a CSR whose values have type code tc
 
@@ -994,30 +996,46 @@ static GrB_Info spgemm_masked(const Csr &A, const Csr &B, const void *aval, cons
 #define K_MSMALL(XT, ZT, A_, M_) masked_hash_kernel<XT, ZT, A_, M_, true><<<(unsigned)ceil_div(n_warp, 8), 256, sm, G.stream>>>(ma)
             GB_FOR_SEMIRING(xt, zt, add, mul, K_MSMALL, err); GB_LAUNCHED();
         }
-        if (n_small) {      // mask rows up to 512 entries: 1024-slot table, 12-16 KB of shared memory, twice the CTAs per SM
-            ma.chunk_row = s_row; ma.chunk_idx = s_idx; ma.chunk_cnt = s_cnt; ma.nchunks = n_small; g.table = MIDSMALL_TABLE;
-            const size_t sm = masked_smem(MIDSMALL_TABLE, 1, wsize);
-#define K_MMIDSMALL(XT, ZT, A_, M_) masked_hash_kernel<XT, ZT, A_, M_, false><<<(unsigned)n_small, 256, sm, G.stream>>>(ma)
-            GB_FOR_SEMIRING(xt, zt, add, mul, K_MMIDSMALL, err); GB_LAUNCHED();
-        }
-        if (n_medium) {
-            ma.chunk_row = m_row; ma.chunk_idx = m_idx; ma.chunk_cnt = m_cnt; ma.nchunks = n_medium; g.table = MEDIUM_TABLE;
-            const size_t sm = masked_smem(MEDIUM_TABLE, 1, wsize);
-#define K_MMEDIUM(XT, ZT, A_, M_) do { \
-            cudaFuncSetAttribute(masked_hash_kernel<XT, ZT, A_, M_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-            masked_hash_kernel<XT, ZT, A_, M_, false><<<(unsigned)n_medium, 256, sm, G.stream>>>(ma); } while (0)
-            GB_FOR_SEMIRING(xt, zt, add, mul, K_MMEDIUM, err); GB_LAUNCHED();
-        }
-        if (n_long) {
-            ma.chunk_row = l_row; ma.chunk_idx = l_idx; ma.chunk_cnt = l_cnt; ma.nchunks = n_long;
-            const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>(n_long, (int64_t)G.num_sms * 2));
-            GB_TRY(dalloc(&g.spa_slot, (size_t)ctas * ncols, err));
-            CU_TRY(cudaMemsetAsync(g.spa_slot, 0xFF, (size_t)ctas * ncols * 4, G.stream), err);
-            GB_TRY(dalloc(&g.queue, 1, err));
-            CU_TRY(cudaMemsetAsync(g.queue, 0, 4, G.stream), err);
-#define K_MSPA(XT, ZT, A_, M_) masked_spa_kernel<XT, ZT, A_, M_><<<ctas, 512, 0, G.stream>>>(ma)
-            GB_FOR_SEMIRING(xt, zt, add, mul, K_MSPA, err); GB_LAUNCHED();
-            dfree(g.spa_slot); dfree(g.queue);
+        // chunked classes: the streaming kernel (spgemm_stream.cuh), persistent CTAs over blocks of consecutive chunks
+        {
+            unsigned int *queues = nullptr;
+            GB_TRY(dalloc(&queues, 4, err));
+            CU_TRY(cudaMemsetAsync(queues, 0, 16, G.stream), err);
+            StreamArgs sa{}; sa.g = g; sa.t_words = words;
+            struct Cls { int64_t n; const int32_t *row; const uint32_t *idx, *cnt; int nt, bm_log2, vals_cap, grab; };
+            const Cls cls[3] = {{n_small, s_row, s_idx, s_cnt, 256, 14, MIDSMALL_TABLE / 2, 8},
+                                {n_medium, m_row, m_idx, m_cnt, 256, 16, MEDIUM_TABLE / 2, 4},
+                                {n_long, l_row, l_idx, l_cnt, 1024, 20, 0, 4}};
+            for (int k = 0; k < 3; ++k) {
+                if (!cls[k].n) continue;
+                sa.chunk_row = cls[k].row; sa.chunk_idx = cls[k].idx; sa.chunk_cnt = cls[k].cnt; sa.nchunks = cls[k].n;
+                sa.queue = queues + k; sa.bm_log2 = cls[k].bm_log2; sa.exact = ncols <= ((int64_t)1 << cls[k].bm_log2) ? 1 : 0;
+                sa.vals_cap = cls[k].vals_cap; sa.table = cls[k].vals_cap * 2; sa.grab = cls[k].grab; sa.spa_slot = nullptr;
+                const size_t sm_var = stream_var_smem(sa.bm_log2, sa.table, sa.vals_cap, wsize);
+                const bool big = cls[k].nt == 1024;
+                int ctas_big = 0;
+                if (big) {      // hub mask rows: the column -> position map of each persistent CTA lives in HBM
+                    ctas_big = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(sa.nchunks, sa.grab), G.num_sms));
+                    GB_TRY(dalloc(&sa.spa_slot, (size_t)ctas_big * ncols, err));
+                    CU_TRY(cudaMemsetAsync(sa.spa_slot, 0xFF, (size_t)ctas_big * ncols * 4, G.stream), err);
+                }
+#define K_MSTREAM(XT, ZT, A_, M_) do { \
+                const size_t sm = sm_var + (big ? stream_fixed_smem<1024, XT, ZT>() : stream_fixed_smem<256, XT, ZT>()); \
+                if (big) { \
+                    auto kern = masked_stream_kernel<1024, XT, ZT, A_, M_>; \
+                    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+                    kern<<<ctas_big, 1024, sm, G.stream>>>(sa); \
+                } else { \
+                    auto kern = masked_stream_kernel<256, XT, ZT, A_, M_>; \
+                    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+                    int per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, sm); \
+                    const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(sa.nchunks, sa.grab), (int64_t)G.num_sms * std::max(per_sm, 1))); \
+                    kern<<<ctas, 256, sm, G.stream>>>(sa); \
+                } } while (0)
+                GB_FOR_SEMIRING(xt, zt, add, mul, K_MSTREAM, err); GB_LAUNCHED();
+                dfree(sa.spa_slot);
+            }
+            dfree(queues);
         }
         dfree(s_row); dfree(s_idx); dfree(s_cnt); dfree(m_row); dfree(m_idx); dfree(m_cnt); dfree(l_row); dfree(l_idx); dfree(l_cnt); dfree(w_rows);
         if (zsz < 4) {      // narrow 32-bit accumulator words to the 1- or 2-byte type, in a second buffer

@@ -186,7 +186,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 template <typename XT> __host__ __device__ constexpr int hot2_stage_bytes(bool need_a) { return RUN * 4 + (need_a ? RUN * (int)sizeof(XT) : 0); }
 constexpr int HOT2_WARPS = 32;
 
-template <typename XT, typename ZT, int ADD, int MUL>
+template <typename XT, typename ZT, int ADD, int MUL, bool PIPE>
 __global__ void __launch_bounds__(HOT2_WARPS * 32, 1) spmv_run_hot2_kernel(const RunArgs p, const Hot2Args h) {
     constexpr bool NEED_A = mul_reads_x(MUL);
     constexpr int STAGE = hot2_stage_bytes<XT>(NEED_A);
@@ -268,8 +268,8 @@ __global__ void __launch_bounds__(HOT2_WARPS * 32, 1) spmv_run_hot2_kernel(const
         if (lane == 0 && r + stride < p.nruns) issue(r + stride);
         spmv_run_gather<XT, MUL, false>(p, r, lane, nvalid, c, L, gather);
     };
-    if constexpr (sizeof(XT) > 4) {
-        // 8-byte values: two runs in flight do not fit in 64 registers per thread -- one at a time
+    if constexpr (sizeof(XT) > 4 || !PIPE) {
+        // one run at a time (8-byte values: two runs in flight do not fit in 64 registers per thread)
         for (; run < p.nruns; run += stride) { fetch(run, cur); spmv_run_fold<XT, ZT, ADD, MUL, false>(p, run, lane, cur); }
         (void)nxt; (void)cur_run;
     } else {
@@ -326,10 +326,16 @@ static void spmv_run_launch(const RunArgs &a, const Hot2Args *hot, size_t table_
             Hot2Args h = *hot;
             h.tab_n = hot2_table_entries<XT>(NEED_A, h.henc, table_limit);
             const size_t smem = (size_t)HOT2_WARPS * hot2_stage_bytes<XT>(NEED_A) + (HOT2_WARPS + 1) * 8 + 8 + (size_t)h.tab_n * sizeof(XT);
-            auto kernel = spmv_run_hot2_kernel<XT, ZT, ADD, MUL>;
-            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             const int ctas = (int)std::min<int64_t>(G.num_sms, ceil_div(a.nruns, HOT2_WARPS));
-            kernel<<<ctas, HOT2_WARPS * 32, smem, G.stream>>>(a, h); GB_LAUNCHED();
+            if (sizeof(XT) <= 4 && tunables().spmv_pipe) {
+                auto kernel = spmv_run_hot2_kernel<XT, ZT, ADD, MUL, true>;
+                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                kernel<<<ctas, HOT2_WARPS * 32, smem, G.stream>>>(a, h); GB_LAUNCHED();
+            } else {
+                auto kernel = spmv_run_hot2_kernel<XT, ZT, ADD, MUL, false>;
+                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                kernel<<<ctas, HOT2_WARPS * 32, smem, G.stream>>>(a, h); GB_LAUNCHED();
+            }
             spmv_run_fixup_kernel<ZT, ADD, false><<<(unsigned)ceil_div(a.nruns * 8, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED();
             return;
         }

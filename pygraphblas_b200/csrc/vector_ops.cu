@@ -433,6 +433,19 @@ extern "C" GrB_Info GrB_Vector_extract(GrB_Vector w, const GrB_Vector mask, cons
     if (mask) GB_VEC_OK(mask, fn);
     if (accum && accum->opcode == OP_USER) return gb_fail(GrB_INVALID_VALUE, nullptr, "%s: user-defined accumulators cannot run on the GPU", fn);
     if (mask && mask->n != w->n) return gb_fail(GrB_DIMENSION_MISMATCH, &w->err, "%s: mask dimension does not match", fn);
+    if (I && I != GrB_ALL && ni == GxB_RANGE && I[0] <= I[1] && I[1] < u->n && I[1] - I[0] + 1 == w->n && w != u && G.have_device) {
+        // a contiguous range (the slice v[a:b] of /root/reference/pygraphblas/base.py:216-252): two device copies, no index list
+        GB_TRY(vector_ensure_device(u));
+        const size_t n = (size_t)w->n, sz = (size_t)tc_size(u->type->code);
+        void *tval = nullptr; uint8_t *tpres = nullptr;
+        GB_TRY(dmalloc(&tval, n * sz + 16, &w->err));
+        CU_TRY(cudaMemcpyAsync(tval, (const uint8_t *)u->dval + (size_t)I[0] * sz, n * sz, cudaMemcpyDeviceToDevice, G.stream), &w->err);
+        if (u->dpres) {
+            GB_TRY(dmalloc((void **)&tpres, n + 16, &w->err));
+            CU_TRY(cudaMemcpyAsync(tpres, u->dpres + I[0], n, cudaMemcpyDeviceToDevice, G.stream), &w->err);
+        }
+        return vector_write(w, mask, accum, desc_flags(desc), tval, tpres, u->type->code, false, nullptr, true);
+    }
     bool all; std::vector<uint64_t> idx;
     GB_TRY(index_list(I, ni, u->n, &all, idx, &w->err, fn));
     if ((all ? u->n : (uint64_t)idx.size()) != w->n) return gb_fail(GrB_DIMENSION_MISMATCH, &w->err, "%s: w has %llu positions, the index list %llu", fn,

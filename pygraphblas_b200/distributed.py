@@ -37,9 +37,10 @@ def local_block_scattered(indptr, indices, values, world, rank):
     n = len(indptr) - 1
     newid = scatter_ids(n)
     lb = -(-n // world)
+    lb = -(-lb // 16) * 16                 # blocks start at multiples of 16 rows: the library moves slices as 16-byte words
     old_of_new = np.empty(n, np.int64)
     old_of_new[newid] = np.arange(n)
-    lo, hi = rank * lb, min((rank + 1) * lb, n)
+    lo, hi = min(rank * lb, n), min((rank + 1) * lb, n)
     rows = old_of_new[lo:hi]
     data = np.ones(len(indices), np.float32) if values is None else values
     S = sp.csr_matrix((data, indices, indptr), shape=(n, n))[rows]

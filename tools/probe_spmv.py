@@ -10,7 +10,7 @@ from bench import cached_graph, spmv_inputs
 
 scale = int(sys.argv[1]) if len(sys.argv) > 1 else 22
 n, indptr, indices = cached_graph(scale)
-vals, u0 = spmv_inputs(scale, len(indices), n)
+vals, u0 = spmv_inputs(len(indices), n)
 A = Matrix.from_csr(indptr, indices, vals, n, n, FP32)
 u = Vector.from_numpy(u0)
 w = Vector.sparse(FP32, n)
@@ -19,7 +19,7 @@ stream = torch.cuda.ExternalStream(int(gb.ffi.cast("uintptr_t", sp_[0])))
 
 def run(label, sr, env):
     keep_run = os.environ.get("B200GRB_SPMV_RUN")
-    for k in ("B200GRB_SPMV_ITEMS", "B200GRB_SPMV_HOT", "B200GRB_HOT_GROUPS", "B200GRB_SPMV_DEBUG", "B200GRB_SPMV_RUN"):
+    for k in ("B200GRB_SPMV_ITEMS", "B200GRB_SPMV_HOT", "B200GRB_HOT_GROUPS", "B200GRB_SPMV_DEBUG", "B200GRB_SPMV_RUN", "B200GRB_SPMV_PIPE"):
         os.environ.pop(k, None)
     if keep_run is not None and "B200GRB_SPMV_RUN" not in env:
         os.environ["B200GRB_SPMV_RUN"] = keep_run
@@ -38,9 +38,11 @@ def run(label, sr, env):
     print(f"{label:44s} {ms*1e3:8.1f} us", flush=True)
 
 if len(sys.argv) > 2 and sys.argv[2] == "sweep":
-    run("default PLUS_TIMES", FP32.PLUS_TIMES, {})
-    for kb in ("0", "16", "32", "48", "64", "80", "96", "100", "112", "120", "128", "130", "136", "144", "160"):
-        run(f"hot table cap {kb}KB PLUS_TIMES", FP32.PLUS_TIMES, {"B200GRB_SPMV_HOT": kb})
+    for rep in range(3):
+        for pipe in ("0", "1"):
+            for kb in ("64", "96", "128"):
+                run(f"rep {rep} pipe={pipe} table cap {kb}KB PLUS_TIMES", FP32.PLUS_TIMES, {"B200GRB_SPMV_HOT": kb, "B200GRB_SPMV_PIPE": pipe})
+    run("plain run kernel (no table, no staging)", FP32.PLUS_TIMES, {"B200GRB_SPMV_HOT": "0"})
     run("default MIN_PLUS", FP32.MIN_PLUS, {})
     run("default PLUS_SECOND", FP32.PLUS_SECOND, {})
     run("PLUS_FIRST (no gather)", FP32.PLUS_FIRST, {})
