@@ -161,6 +161,7 @@ struct Tunables {
     int spmv_hot_kb = -1;      // B200GRB_SPMV_HOT     -1 default (on when the gathers are concentrated), 0 off, >0 table cap in KB
     bool no_pull = false, no_push = false, force_push = false, spmv_debug = false;
     bool spmv_pipe = false;    // B200GRB_SPMV_PIPE    software-pipeline two runs per warp in the hot-table kernel (4-byte types)
+    bool spgemm_trace = false; // B200GRB_SPGEMM_TRACE phase times of GrB_mxm (masked) on stderr
     int spgemm_v = 0;          // B200GRB_SPGEMM_V     masked SpGEMM kernel generation (0 = default)
 };
 const Tunables &tunables();
@@ -182,6 +183,15 @@ template <typename T> static inline GrB_Info dalloc(T **p, size_t count, std::st
 }
 void csr_free(Csr &c);
 void csr_drop_plans(Csr &c);
+// Persistent scratch of the compute calls: slot k keeps its buffer between calls and only grows (calls are serialised on one
+// stream, so a slot is never in use twice).  Large transient cudaMallocAsync / cudaFreeAsync pairs were measured to cost
+// 10-70 ms per call when the pool has to map fresh memory (masked GrB_mxm: 620 MB of column maps) -- these buffers never leave.
+enum WsSlot : int { WS_WORDS = 0, WS_FOUND, WS_FLOPS, WS_TOTAL, WS_CS, WS_CM, WS_CL, WS_C1, WS_SROW, WS_SIDX, WS_SCNT, WS_MROW, WS_MIDX, WS_MCNT,
+                    WS_LROW, WS_LIDX, WS_LCNT, WS_WROWS, WS_QUEUES, WS_SPA_SLOT, WS_COUNT };
+GrB_Info ws_get(int slot, void **p, size_t bytes, std::string *err, bool *fresh = nullptr);
+template <typename T> static inline GrB_Info ws_array(int slot, T **p, size_t count, std::string *err, bool *fresh = nullptr) {
+    return ws_get(slot, (void **)p, count * sizeof(T) + 16, err, fresh);
+}
 
 // host <-> device sync of containers (objects.cu)
 GrB_Info matrix_flush_pending(GrB_Matrix A);

@@ -937,6 +937,21 @@ static GrB_Info spgemm_unmasked(const Csr &A, const Csr &B, const void *aval, co
 static constexpr int64_t CHUNK_FLOPS = 32768;     // flop budget of one CTA-level work unit
 static constexpr int WARP_FLOPS = 2048;           // rows at most this heavy (and with short mask rows) run warp-per-row
 
+// B200GRB_SPGEMM_TRACE=1: device time of the phases of one masked call (events on the compute stream), printed to stderr
+struct PhaseTrace {
+    bool on; std::vector<cudaEvent_t> ev; std::vector<const char *> name;
+    PhaseTrace() : on(tunables().spgemm_trace) { mark("start"); }
+    void mark(const char *n) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, G.stream); ev.push_back(e); name.push_back(n); }
+    ~PhaseTrace() {
+        if (!on) return;
+        cudaStreamSynchronize(G.stream);
+        fprintf(stderr, "[mxm phases]");
+        for (size_t k = 1; k < ev.size(); ++k) { float ms = 0; cudaEventElapsedTime(&ms, ev[k - 1], ev[k]); fprintf(stderr, " %s %.2f ms |", name[k], ms); }
+        float tot = 0; cudaEventElapsedTime(&tot, ev.front(), ev.back()); fprintf(stderr, " total %.2f ms\n", tot);
+        for (auto e : ev) cudaEventDestroy(e);
+    }
+};
+
 static GrB_Info spgemm_masked(const Csr &A, const Csr &B, const void *aval, const void *bval, int xt, int zt,
                               int add, int mul, bool need_a, bool need_b, const Csr &M, int mtc, bool m_struct,
                               bool dot, Csr &T, std::string *err) {
@@ -948,9 +963,11 @@ static GrB_Info spgemm_masked(const Csr &A, const Csr &B, const void *aval, cons
     g.a_ptr = A.rowptr32; g.a_col = A.col; g.a_val = aval; g.b_ptr = B.rowptr32; g.b_col = B.col; g.b_val = bval;
     g.m_ptr = M.rowptr32; g.m_col = M.col; g.m_val = M.val; g.m_tc = mtc; g.m_struct = m_struct;
     g.nrows = nrows; g.ncols = ncols; g.add_op = add; g.mul_op = mul; g.need_a = need_a; g.need_b = need_b;
+    PhaseTrace trace;
+    bool words_owned = false;
     void *words = nullptr; uint8_t *found = nullptr;          // per mask entry: accumulator word, "has a value"
-    GB_TRY(dmalloc(&words, (size_t)M.nnz * wsize + 16, err));
-    GB_TRY(dmalloc((void **)&found, (size_t)M.nnz + 16, err));
+    GB_TRY(ws_get(WS_WORDS, &words, (size_t)M.nnz * wsize + 16, err));
+    GB_TRY(ws_get(WS_FOUND, (void **)&found, (size_t)M.nnz + 16, err));
     g.c_val = words; g.t_found = found; ma.t_words = words;
     G.last_flops = 0;
     if (M.nnz > 0 && dot) {
@@ -959,7 +976,7 @@ static GrB_Info spgemm_masked(const Csr &A, const Csr &B, const void *aval, cons
         GB_FOR_SEMIRING(xt, zt, add, mul, K_DOT, err); GB_LAUNCHED();
     } else if (M.nnz > 0) {
         int64_t *flops = nullptr; unsigned long long *total = nullptr;
-        GB_TRY(dalloc(&flops, (size_t)nrows, err)); GB_TRY(dalloc(&total, 1, err));
+        GB_TRY(ws_array(WS_FLOPS, &flops, (size_t)nrows, err)); GB_TRY(ws_array(WS_TOTAL, &total, 1, err));
         CU_TRY(cudaMemsetAsync(total, 0, 8, G.stream), err);
         flops_kernel<<<grid_for(nrows * 32), 256, 0, G.stream>>>(A.rowptr32, A.col, B.rowptr32, nrows, flops, total); GB_LAUNCHED();
         // accumulators start at the identity, flags at 0
@@ -968,8 +985,8 @@ static GrB_Info spgemm_masked(const Csr &A, const Csr &B, const void *aval, cons
         GB_FOR_SEMIRING(xt, zt, add, mul, K_IDENT, err); GB_LAUNCHED();
         // classify rows and cut heavy ones into flop-bounded chunks
         int64_t *cs = nullptr, *cm = nullptr, *cl = nullptr, *c1 = nullptr;
-        GB_TRY(dalloc(&cs, (size_t)nrows + 1, err));
-        GB_TRY(dalloc(&cm, (size_t)nrows + 1, err)); GB_TRY(dalloc(&cl, (size_t)nrows + 1, err)); GB_TRY(dalloc(&c1, (size_t)nrows + 1, err));
+        GB_TRY(ws_array(WS_CS, &cs, (size_t)nrows + 1, err));
+        GB_TRY(ws_array(WS_CM, &cm, (size_t)nrows + 1, err)); GB_TRY(ws_array(WS_CL, &cl, (size_t)nrows + 1, err)); GB_TRY(ws_array(WS_C1, &c1, (size_t)nrows + 1, err));
         CU_TRY(cudaMemsetAsync(cs + nrows, 0, 8, G.stream), err);
         CU_TRY(cudaMemsetAsync(cm + nrows, 0, 8, G.stream), err); CU_TRY(cudaMemsetAsync(cl + nrows, 0, 8, G.stream), err);
         CU_TRY(cudaMemsetAsync(c1 + nrows, 0, 8, G.stream), err);
@@ -984,12 +1001,12 @@ static GrB_Info spgemm_masked(const Csr &A, const Csr &B, const void *aval, cons
         G.last_flops = (uint64_t)tf;
         int32_t *s_row = nullptr, *m_row = nullptr, *l_row = nullptr, *w_rows = nullptr;
         uint32_t *s_idx = nullptr, *s_cnt = nullptr, *m_idx = nullptr, *m_cnt = nullptr, *l_idx = nullptr, *l_cnt = nullptr;
-        GB_TRY(dalloc(&s_row, (size_t)n_small, err)); GB_TRY(dalloc(&s_idx, (size_t)n_small, err)); GB_TRY(dalloc(&s_cnt, (size_t)n_small, err));
-        GB_TRY(dalloc(&m_row, (size_t)n_medium, err)); GB_TRY(dalloc(&m_idx, (size_t)n_medium, err)); GB_TRY(dalloc(&m_cnt, (size_t)n_medium, err));
-        GB_TRY(dalloc(&l_row, (size_t)n_long, err)); GB_TRY(dalloc(&l_idx, (size_t)n_long, err)); GB_TRY(dalloc(&l_cnt, (size_t)n_long, err));
-        GB_TRY(dalloc(&w_rows, (size_t)n_warp, err));
+        GB_TRY(ws_array(WS_SROW, &s_row, (size_t)n_small, err)); GB_TRY(ws_array(WS_SIDX, &s_idx, (size_t)n_small, err)); GB_TRY(ws_array(WS_SCNT, &s_cnt, (size_t)n_small, err));
+        GB_TRY(ws_array(WS_MROW, &m_row, (size_t)n_medium, err)); GB_TRY(ws_array(WS_MIDX, &m_idx, (size_t)n_medium, err)); GB_TRY(ws_array(WS_MCNT, &m_cnt, (size_t)n_medium, err));
+        GB_TRY(ws_array(WS_LROW, &l_row, (size_t)n_long, err)); GB_TRY(ws_array(WS_LIDX, &l_idx, (size_t)n_long, err)); GB_TRY(ws_array(WS_LCNT, &l_cnt, (size_t)n_long, err));
+        GB_TRY(ws_array(WS_WROWS, &w_rows, (size_t)n_warp, err));
         chunk_fill_kernel<<<grid_for(nrows), 256, 0, G.stream>>>(cs, cm, cl, c1, nrows, s_row, s_idx, s_cnt, m_row, m_idx, m_cnt, l_row, l_idx, l_cnt, w_rows); GB_LAUNCHED();
-        dfree(flops); dfree(total); dfree(cs); dfree(cm); dfree(cl); dfree(c1);
+        trace.mark("flops + chunk lists");
         if (n_warp) {
             g.rows = w_rows; g.nbin = n_warp; g.table = SMALL_TABLE;
             const size_t sm = masked_smem(SMALL_TABLE, 8, wsize);
@@ -999,13 +1016,14 @@ static GrB_Info spgemm_masked(const Csr &A, const Csr &B, const void *aval, cons
         // chunked classes: the streaming kernel (spgemm_stream.cuh), persistent CTAs over blocks of consecutive chunks
         {
             unsigned int *queues = nullptr;
-            GB_TRY(dalloc(&queues, 4, err));
+            GB_TRY(ws_array(WS_QUEUES, &queues, 4, err));
             CU_TRY(cudaMemsetAsync(queues, 0, 16, G.stream), err);
             StreamArgs sa{}; sa.g = g; sa.t_words = words;
             struct Cls { int64_t n; const int32_t *row; const uint32_t *idx, *cnt; int nt, bm_log2, vals_cap, grab; };
             const Cls cls[3] = {{n_small, s_row, s_idx, s_cnt, 256, 14, MIDSMALL_TABLE / 2, 8},
                                 {n_medium, m_row, m_idx, m_cnt, 256, 16, MEDIUM_TABLE / 2, 4},
                                 {n_long, l_row, l_idx, l_cnt, 1024, 20, 0, 4}};
+            trace.mark("warp class");
             for (int k = 0; k < 3; ++k) {
                 if (!cls[k].n) continue;
                 sa.chunk_row = cls[k].row; sa.chunk_idx = cls[k].idx; sa.chunk_cnt = cls[k].cnt; sa.nchunks = cls[k].n;
@@ -1016,8 +1034,9 @@ static GrB_Info spgemm_masked(const Csr &A, const Csr &B, const void *aval, cons
                 int ctas_big = 0;
                 if (big) {      // hub mask rows: the column -> position map of each persistent CTA lives in HBM
                     ctas_big = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(sa.nchunks, sa.grab), G.num_sms));
-                    GB_TRY(dalloc(&sa.spa_slot, (size_t)ctas_big * ncols, err));
-                    CU_TRY(cudaMemsetAsync(sa.spa_slot, 0xFF, (size_t)ctas_big * ncols * 4, G.stream), err);
+                    bool fresh = false;          // the kernel resets every entry it sets: the maps stay all -1 between calls
+                    GB_TRY(ws_array(WS_SPA_SLOT, &sa.spa_slot, (size_t)ctas_big * ncols, err, &fresh));
+                    if (fresh) CU_TRY(cudaMemsetAsync(sa.spa_slot, 0xFF, ((size_t)ctas_big * ncols + ((size_t)ctas_big * ncols) / 4) * 4, G.stream), err);
                 }
 #define K_MSTREAM(XT, ZT, A_, M_) do { \
                 const size_t sm = sm_var + (big ? stream_fixed_smem<1024, XT, ZT>() : stream_fixed_smem<256, XT, ZT>()); \
@@ -1033,16 +1052,14 @@ static GrB_Info spgemm_masked(const Csr &A, const Csr &B, const void *aval, cons
                     kern<<<ctas, 256, sm, G.stream>>>(sa); \
                 } } while (0)
                 GB_FOR_SEMIRING(xt, zt, add, mul, K_MSTREAM, err); GB_LAUNCHED();
-                dfree(sa.spa_slot);
+                trace.mark(k == 0 ? "stream S" : (k == 1 ? "stream M" : "stream L"));
             }
-            dfree(queues);
         }
-        dfree(s_row); dfree(s_idx); dfree(s_cnt); dfree(m_row); dfree(m_idx); dfree(m_cnt); dfree(l_row); dfree(l_idx); dfree(l_cnt); dfree(w_rows);
         if (zsz < 4) {      // narrow 32-bit accumulator words to the 1- or 2-byte type, in a second buffer
             void *typed = nullptr;
             GB_TRY(dmalloc(&typed, (size_t)M.nnz * zsz + 16, err));
             narrow_words_kernel<<<grid_for(M.nnz), 256, 0, G.stream>>>((const uint32_t *)words, (uint8_t *)typed, (int)zsz, M.nnz); GB_LAUNCHED();
-            dfree(words); words = typed;
+            words = typed; words_owned = true;
         }
     }
     void *tval = words;
@@ -1059,8 +1076,9 @@ static GrB_Info spgemm_masked(const Csr &A, const Csr &B, const void *aval, cons
         row_found_fill_kernel<<<grid_for(nrows * 32), 256, 0, G.stream>>>(M.rowptr32, M.col, found, (const uint8_t *)tval, (int)zsz,
                                                                           nrows, T.rowptr, T.col, (uint8_t *)T.val); GB_LAUNCHED();
     }
-    dfree(tval); dfree(found);
+    if (words_owned) dfree(tval);
     GB_TRY(dev_build_rowptr32(T, err));
+    trace.mark("compaction");
     CU_TRY(cudaGetLastError(), err);
     return GrB_SUCCESS;
 }

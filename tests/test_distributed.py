@@ -117,3 +117,51 @@ def test_row_block_allgather_world2(tmp_path):
     assert b[0] == 0 and b[-1] == n and np.all(np.diff(b) >= 0)
     per = np.diff(indptr[b])
     assert per.max() <= 1.3 * per.mean() + indptr[1:].max()
+
+
+# ------------------------------------------------------------------ the in-library exchange (csrc/dist.cu): host-side control plane
+def _worker_handles(rank, world, port, out):
+    import torch.distributed as dist
+    from pygraphblas_b200.distributed import exchange_handles
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = bytes([rank + 1]) * 64                       # stands for this rank's 64-byte CUDA-IPC handle
+    allh = exchange_handles(mine, world, rank)
+    ok = len(allh) == 64 * world and all(allh[64 * r:64 * (r + 1)] == bytes([r + 1]) * 64 for r in range(world))
+    np.save(out + f".{rank}.npy", np.array([ok]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ipc_handle_exchange_world2(tmp_path):
+    """Every rank ends up with all ranks' 64-byte handles in rank order (what B200_Comm_connect takes)."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "h")
+    mp.spawn(_worker_handles, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert all(bool(np.load(out + f".{r}.npy")[0]) for r in range(2))
+
+
+def test_equal_row_blocks_are_aligned_and_cover():
+    from pygraphblas_b200.distributed import equal_row_blocks, local_block_scattered
+    from pygraphblas_b200.generators import rmat_csr
+    for n, world in ((1 << 22, 8), (1000, 3), (17, 2), (5, 8)):
+        b = equal_row_blocks(n, world)
+        assert b[0] == 0 and b[-1] == n and len(b) == world + 1 and all(x <= y for x, y in zip(b, b[1:]))
+        assert all(x % 16 == 0 or x == n for x in b[:-1])        # the library moves slices as 16-byte words (empty trailing blocks start at n)
+    n, indptr, indices = rmat_csr(10, 8, seed=3)
+    for world in (2, 3, 8):
+        parts = [local_block_scattered(indptr, indices, None, world, r) for r in range(world)]
+        lb = parts[0][1]
+        assert lb % 16 == 0 and world * lb >= n
+        assert sum(len(p[3]) for p in parts) == len(indices)          # every entry lands in exactly one block
+
+
+def test_comm_refuses_without_a_gpu():
+    """The exchange runs only over GPU peer memory: without a device the communicator refuses (no CPU fallback)."""
+    import pygraphblas_b200 as gb
+    if gb.have_device():
+        pytest.skip("needs a machine without a CUDA device")
+    from pygraphblas_b200.distributed import Comm
+    with pytest.raises(gb.Panic):
+        Comm(1024, gb.FP32, 0, 1)

@@ -266,3 +266,63 @@ def test_dense_fill_like_the_reference_test_pow():
     assert lib.GrB_Matrix_assign_UINT8(m._matrix[0], gb.ffi.NULL, gb.ffi.NULL, 1, lib.GrB_ALL, 0, lib.GrB_ALL, 0, gb.ffi.NULL) == 0
     assert m.nvals == 100 and set(m.to_arrays()[2].tolist()) == {1}
     assert (m @ m).iseq(m ** 2) and set((m ** 3).to_arrays()[2].tolist()) == {100}
+
+
+# ------------------------------------------------------------------ GrB_Matrix_extract / GxB_*_diag / kronecker (matrix_assign.cu) against scipy
+def _sp(m):
+    I, J, X = m.to_arrays()
+    return sp.csr_matrix((X.astype(np.float64), (I.astype(np.int64), J.astype(np.int64))), shape=(m.nrows, m.ncols))
+
+
+def _rand_int_matrix(rng, nr, nc, dens):
+    k = int(round(nr * nc * dens))
+    flat = rng.choice(nr * nc, size=k, replace=False)
+    return Matrix.from_lists(flat // nc, flat % nc, rng.integers(1, 9, k), nr, nc, INT64)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_matrix_extract_against_scipy(seed):
+    """C = A(I, J) for GrB_ALL, ranges, sorted lists, unsorted lists with duplicates, and INP0 = TRAN."""
+    rng = np.random.default_rng(700 + seed)
+    nr, nc = int(rng.integers(4, 30)), int(rng.integers(4, 30))
+    A = _rand_int_matrix(rng, nr, nc, 0.3)
+    tran = seed % 4 == 3
+    S = _sp(A).T.tocsr() if tran else _sp(A)
+    an, am = S.shape
+    ffi = gb.ffi
+    if seed % 3 == 0:
+        I, Iarg, ni = np.arange(an), lib.GrB_ALL, 0
+    elif seed % 3 == 1:
+        I = rng.integers(0, an, 5); Iarg = ffi.new("GrB_Index[]", I.tolist()); ni = 5                  # duplicates allowed
+    else:
+        lo, hi = sorted(rng.integers(0, an, 2).tolist()); I = np.arange(lo, hi + 1); Iarg = ffi.new("GrB_Index[]", [lo, hi]); ni = lib.GxB_RANGE
+    if seed % 4 == 0:
+        J, Jarg, nj = np.arange(am), lib.GrB_ALL, 0
+    elif seed % 4 == 1:
+        J = np.sort(rng.choice(am, size=min(4, am), replace=False)); Jarg = ffi.new("GrB_Index[]", J.tolist()); nj = len(J)
+    else:
+        J = rng.integers(0, am, 6); Jarg = ffi.new("GrB_Index[]", J.tolist()); nj = 6                    # unsorted, duplicates
+    C = Matrix.sparse(INT64, len(I), len(J))
+    desc = descriptor.T0.get_desc() if tran else ffi.NULL
+    assert lib.GrB_Matrix_extract(C._matrix[0], ffi.NULL, ffi.NULL, A._matrix[0], Iarg, ni, Jarg, nj, desc) == 0, ffi.string(lib.B200_last_error())
+    ref = S[I][:, J].tocsr(); ref.sort_indices()
+    got = _sp(C); got.sort_indices()
+    assert (got != ref).nnz == 0 and got.nnz == ref.nnz
+
+
+def test_diag_and_kronecker_against_scipy():
+    rng = np.random.default_rng(9)
+    v = Vector.from_lists([0, 2, 3], [5, 7, 9], 5, INT64)
+    for k in (0, 2, -1):
+        n = 5 + abs(k)
+        C = Matrix.sparse(INT64, n, n)
+        assert lib.GxB_Matrix_diag(C._matrix[0], v._vector[0], k, gb.ffi.NULL) == 0
+        ref = sp.diags([np.array([5, 0, 7, 9, 0], np.float64)], [k], shape=(n, n)).tocsr(); ref.eliminate_zeros()
+        assert (_sp(C) != ref).nnz == 0
+        w = Vector.sparse(INT64, 5)
+        assert lib.GxB_Vector_diag(w._vector[0], C._matrix[0], k, gb.ffi.NULL) == 0
+        assert w.to_lists() == [[0, 2, 3], [5, 7, 9]]
+    A, B = _rand_int_matrix(rng, 4, 5, 0.5), _rand_int_matrix(rng, 3, 6, 0.4)
+    C = Matrix.sparse(INT64, 12, 30)
+    assert lib.GrB_Matrix_kronecker_BinaryOp(C._matrix[0], gb.ffi.NULL, gb.ffi.NULL, INT64.TIMES.get_op(), A._matrix[0], B._matrix[0], gb.ffi.NULL) == 0
+    assert (_sp(C) != sp.kron(_sp(A), _sp(B)).tocsr()).nnz == 0
