@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200grb.so")
 SOURCES = ["objects.cu", "device_ops.cu", "spmv.cu", "spmv_run.cu", "spmv_run_int.cu", "spmv_run_generic.cu", "spmv_pull.cu",
-           "spgemm.cu", "vector_ops.cu", "matrix_ops.cu", "matrix_assign.cu", "dist.cu", "compat.cu"]
+           "spgemm.cu", "vector_ops.cu", "matrix_ops.cu", "matrix_assign.cu", "dist.cu", "hyper.cu", "compat.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-diag-suppress", "186,177,550"]
 

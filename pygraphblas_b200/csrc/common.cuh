@@ -162,6 +162,7 @@ struct Tunables {
     bool no_pull = false, no_push = false, force_push = false, spmv_debug = false;
     bool spmv_pipe = false;    // B200GRB_SPMV_PIPE    software-pipeline two runs per warp in the hot-table kernel (4-byte types)
     bool spgemm_trace = false; // B200GRB_SPGEMM_TRACE phase times of GrB_mxm (masked) on stderr
+    int stream_blk_log2 = 8;   // B200GRB_STREAM_BLK   log2 of the block of a long B row one warp takes (masked SpGEMM)
     int spgemm_v = 0;          // B200GRB_SPGEMM_V     masked SpGEMM kernel generation (0 = default)
 };
 const Tunables &tunables();
@@ -209,6 +210,13 @@ bool gb_valid_matrix(const GrB_Matrix A);
 bool gb_valid_vector(const GrB_Vector v);
 
 struct DescFlags { bool replace, mask_comp, mask_struct, tran0, tran1; int axb; };
+// hypersparse operands (dimension beyond 2^31-1): computed on in their compact index space (hyper.cu)
+bool gb_hyper_matrix(const GrB_Matrix A);
+bool gb_hyper_vector(const GrB_Vector v);
+GrB_Info hyper_mxv(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp accum, const GrB_Semiring s, const GrB_Matrix A, const GrB_Vector u,
+                   const GrB_Descriptor desc, bool vxm);
+GrB_Info hyper_mxm(GrB_Matrix C, const GrB_Matrix Mask, const GrB_BinaryOp accum, const GrB_Semiring s, const GrB_Matrix A, const GrB_Matrix B,
+                   const GrB_Descriptor desc);
 DescFlags desc_flags(const GrB_Descriptor d);
 
 // w<mask> = accum(w, T) on the device (vector_ops.cu).  T = (tval, tpres) of type ttc over w->n positions

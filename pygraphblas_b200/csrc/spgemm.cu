@@ -1029,6 +1029,7 @@ static GrB_Info spgemm_masked(const Csr &A, const Csr &B, const void *aval, cons
                 sa.chunk_row = cls[k].row; sa.chunk_idx = cls[k].idx; sa.chunk_cnt = cls[k].cnt; sa.nchunks = cls[k].n;
                 sa.queue = queues + k; sa.bm_log2 = cls[k].bm_log2; sa.exact = ncols <= ((int64_t)1 << cls[k].bm_log2) ? 1 : 0;
                 sa.vals_cap = cls[k].vals_cap; sa.table = cls[k].vals_cap * 2; sa.grab = cls[k].grab; sa.spa_slot = nullptr;
+                sa.blk_log2 = tunables().stream_blk_log2;
                 const size_t sm_var = stream_var_smem(sa.bm_log2, sa.table, sa.vals_cap, wsize);
                 const bool big = cls[k].nt == 1024;
                 int ctas_big = 0;
@@ -1039,18 +1040,14 @@ static GrB_Info spgemm_masked(const Csr &A, const Csr &B, const void *aval, cons
                     if (fresh) CU_TRY(cudaMemsetAsync(sa.spa_slot, 0xFF, ((size_t)ctas_big * ncols + ((size_t)ctas_big * ncols) / 4) * 4, G.stream), err);
                 }
 #define K_MSTREAM(XT, ZT, A_, M_) do { \
-                const size_t sm = sm_var + (big ? stream_fixed_smem<1024, XT, ZT>() : stream_fixed_smem<256, XT, ZT>()); \
-                if (big) { \
-                    auto kern = masked_stream_kernel<1024, XT, ZT, A_, M_>; \
-                    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-                    kern<<<ctas_big, 1024, sm, G.stream>>>(sa); \
-                } else { \
-                    auto kern = masked_stream_kernel<256, XT, ZT, A_, M_>; \
-                    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-                    int per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, sm); \
-                    const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(sa.nchunks, sa.grab), (int64_t)G.num_sms * std::max(per_sm, 1))); \
-                    kern<<<ctas, 256, sm, G.stream>>>(sa); \
-                } } while (0)
+                const int nt = big ? 1024 : 256; \
+                const size_t sm = sm_var + stream_fixed_smem<XT>(nt); \
+                auto kern = masked_stream_kernel<XT, ZT, A_, M_>; \
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+                int ctas = ctas_big; \
+                if (!big) { int per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, sm); \
+                            ctas = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(sa.nchunks, sa.grab), (int64_t)G.num_sms * std::max(per_sm, 1))); } \
+                kern<<<ctas, nt, sm, G.stream>>>(sa); } while (0)
                 GB_FOR_SEMIRING(xt, zt, add, mul, K_MSTREAM, err); GB_LAUNCHED();
                 trace.mark(k == 0 ? "stream S" : (k == 1 ? "stream M" : "stream L"));
             }
@@ -1156,6 +1153,7 @@ extern "C" GrB_Info GrB_mxm(GrB_Matrix C, const GrB_Matrix Mask, const GrB_Binar
     if (!gb_valid_matrix(C) || !gb_valid_matrix(A) || !gb_valid_matrix(B) || (Mask && !gb_valid_matrix(Mask)) || semiring->magic != GB_MAGIC)
         return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "GrB_mxm: invalid object");
     std::string *err = &C->err;
+    if (gb_hyper_matrix(A) || gb_hyper_matrix(B) || gb_hyper_matrix(C)) return hyper_mxm(C, Mask, accum, semiring, A, B, desc);
     const DescFlags f = desc_flags(desc);
     const GrB_BinaryOp mulop = semiring->mul, addop = semiring->add->op;
     if (mulop->opcode == OP_USER || addop->opcode == OP_USER || (accum && accum->opcode == OP_USER))

@@ -530,6 +530,7 @@ extern "C" GrB_Info GrB_mxv(GrB_Vector w, const GrB_Vector mask, const GrB_Binar
                             const GrB_Matrix A, const GrB_Vector u, const GrB_Descriptor desc) {
     GB_LOCK; GB_CHECK_INIT;
     GB_TRY(mxv_check(w, mask, semiring, A, u, "GrB_mxv"));
+    if (gb_hyper_matrix(A) || gb_hyper_vector(u) || gb_hyper_vector(w)) return hyper_mxv(w, mask, accum, semiring, A, u, desc, false);
     const DescFlags f = desc_flags(desc);
     return mxv_core(w, mask, accum, semiring, A, u, f, /*use_transpose=*/f.tran0, /*flip=*/false, "GrB_mxv");
 }
@@ -538,6 +539,7 @@ extern "C" GrB_Info GrB_vxm(GrB_Vector w, const GrB_Vector mask, const GrB_Binar
                             const GrB_Vector u, const GrB_Matrix A, const GrB_Descriptor desc) {
     GB_LOCK; GB_CHECK_INIT;
     GB_TRY(mxv_check(w, mask, semiring, A, u, "GrB_vxm"));
+    if (gb_hyper_matrix(A) || gb_hyper_vector(u) || gb_hyper_vector(w)) return hyper_mxv(w, mask, accum, semiring, A, u, desc, true);
     const DescFlags f = desc_flags(desc);
     // w' = u'A  <=>  w = A'u: pull along the rows of A' (INP1 = TRAN cancels the transpose)
     return mxv_core(w, mask, accum, semiring, A, u, f, /*use_transpose=*/!f.tran1, /*flip=*/true, "GrB_vxm");

@@ -450,3 +450,50 @@ def test_hot_calls_from_a_thread_pool():
 
     with ThreadPoolExecutor(8) as ex:
         assert sorted(ex.map(work, range(48))) == list(range(48))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_hypersparse_operands_compute_in_their_compact_space(seed):
+    """Unsized objects are 2^60 x 2^60 like the reference's (matrix.py:167-170); their mxv / vxm / mxm must give what the
+    same tuples give in a small sized space (ids spread over the 2^60 range), for masks / accumulators / descriptors."""
+    rng = np.random.default_rng(4000 + seed)
+    n = 24
+    big = np.sort(rng.choice(1 << 59, size=n, replace=False).astype(np.uint64)) + np.uint64(1 << 33)     # the big id of small id k
+    typ = ["INT64", "FP64", "BOOL", "UINT8"][seed % 4]
+    A = util.rand_mat(rng, typ, n, n, 0.3)
+    B = util.rand_mat(rng, typ, n, n, 0.3)
+    u = util.rand_vec(rng, typ, n, 0.6)
+    w = util.rand_vec(rng, typ, n, 0.4)
+    M = util.rand_mat(rng, "BOOL", n, n, 0.5)
+    m = util.rand_vec(rng, "BOOL", n, 0.5)
+    desc = ["", "T0", "RC", "S", "T1", "RSC", "T0T1", "C"][seed]
+    srs = util.semirings_for(typ)
+    sr = srs[seed % len(srs)]
+    accum = ("PLUS" if typ != "BOOL" else "LOR", typ) if seed % 2 else None
+    T = gb.types.by_name(typ)
+
+    def big_mat(d):
+        return Matrix.from_lists(big[np.array(d["I"], np.int64)] if d["I"] else [], big[np.array(d["J"], np.int64)] if d["J"] else [], d["X"],
+                                 1 << 60, 1 << 60, gb.types.by_name(d["type"]))
+
+    def big_vec(d):
+        return Vector.from_lists(big[np.array(d["I"], np.int64)] if d["I"] else [], d["X"], 1 << 60, gb.types.by_name(d["type"]))
+
+    gsr, gacc, gdesc = util.g_semiring(sr), util.g_accum(accum), util.g_desc(desc)
+    use_mask = seed % 3 != 0
+    # mxv / vxm
+    for op in ("mxv", "vxm"):
+        case = {"op": op, "A": A, "u": u, "w": w, "mask": m if use_mask else None, "accum": accum, "semiring": list(sr), "desc": desc}
+        small = util.product_run(case)
+        Ab, ub, wb, mb = big_mat(A), big_vec(u), big_vec(w), (big_vec(m) if use_mask else None)
+        out = Ab.mxv(ub, semiring=gsr, out=wb, mask=mb, accum=gacc, desc=gdesc) if op == "mxv" else ub.vxm(Ab, semiring=gsr, out=wb, mask=mb, accum=gacc, desc=gdesc)
+        assert out.size == 1 << 60
+        I, X = out.to_arrays()
+        assert np.array_equal(I, big[np.asarray(small.I, np.int64)]) and np.array_equal(X, small.X), (op, desc)
+    # mxm
+    case = {"op": "mxm", "A": A, "B": B, "C": util.rand_mat(rng, typ, n, n, 0.2), "mask": M if use_mask else None, "accum": accum, "semiring": list(sr), "desc": desc}
+    small = util.product_run(case)
+    Cb = big_mat(case["C"])
+    out = big_mat(A).mxm(big_mat(B), semiring=gsr, out=Cb, mask=big_mat(M) if use_mask else None, accum=gacc, desc=gdesc)
+    I, J, X = out.to_arrays()
+    assert np.array_equal(I, big[np.asarray(small.I, np.int64)]) and np.array_equal(J, big[np.asarray(small.J, np.int64)]) and np.array_equal(X, small.X), desc

@@ -8,3 +8,5 @@ ncu -i gpurun_out/k_prof.ncu-rep --page source --csv --print-source sass 2>/dev/
 ncu -i gpurun_out/k_prof.ncu-rep --page source --csv --print-source cuda 2>/dev/null | cut -c1-700 > gpurun_out/k_prof_cuda.csv
 rm -f gpurun_out/k_prof.ncu-rep
 ls -la gpurun_out/k_prof*; tail -3 gpurun_out/k_ncu.log
+echo "== 1/8 block probe"; timeout 600 python tools/probe_block.py 8 > gpurun_out/k_block.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/k_block.log
+echo "== pytest new (hyper, extract, assign, ref suite)"; timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_matrix_ops_gpu.py tests/test_reference_gpu.py -q -m gpu --maxfail=10 -p no:cacheprovider -k "hyper or extract or diag or assign or reference" > gpurun_out/k_pytest.log 2>&1; echo "rc=$?"; tail -12 gpurun_out/k_pytest.log; grep -c passed gpurun_out/reference_suite_on_gpu.txt; tail -12 gpurun_out/reference_suite_on_gpu.txt

@@ -15,16 +15,16 @@ scale = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 mode = sys.argv[3] if len(sys.argv) > 3 else "masked"
 n, indptr, indices = cached_graph(scale)
-if mode == "masked":
+if mode.startswith("masked"):
     S = sp.csr_matrix((np.ones(len(indices), np.int8), indices, indptr), shape=(n, n))
     Ls = sp.tril(S + S.T, -1).tocsr(); Ls.sort_indices()
     L = Matrix.from_csr(Ls.indptr.astype(np.int64), Ls.indices.astype(np.uint32), np.ones(Ls.nnz, np.int64), n, n, INT64)
-    for dname in ("S", "ST1"):
+    for dname in (("S",) if mode == "masked_S" else ("S", "ST1")):
         for _ in range(reps):
             gb.lib.B200_device_synchronize(); t0 = time.perf_counter()
             C = L.mxm(L, mask=L, semiring=INT64.PLUS_PAIR, desc=getattr(descriptor, dname))
             gb.lib.B200_device_synchronize(); dt = time.perf_counter() - t0
-            print(f"masked {dname} scale {scale}: {dt*1e3:.2f} ms, nnz_out {C.nvals}, triangles {int(C.to_arrays()[2].sum())}", flush=True)
+            print(f"masked {dname} scale {scale}: {dt*1e3:.2f} ms wall (incl. freeing the previous result), nnz_out {C.nvals}", flush=True)
 else:
     vals = np.ones(len(indices), np.float32)
     A = Matrix.from_csr(indptr, indices, vals, n, n, FP32)
