@@ -142,9 +142,11 @@ GrB_Info gb_fail(GrB_Info code, std::string *where, const char *fmt, ...);
 
 // every entry point: take the library lock and make the library's device current for the calling host thread
 // (the reference drives `lib` from a ThreadPool, /root/reference/demo/dnn/challenge.py:48-51; a new thread starts on device 0)
-extern thread_local int tl_cuda_device;
 static inline void gb_thread_enter() {
-    if (G.have_device && tl_cuda_device != G.device) { cudaSetDevice(G.device); tl_cuda_device = G.device; }
+    // the embedding application (torch, another library) may have switched this thread to another GPU since the last call:
+    // ask, do not cache
+    if (G.have_device) { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != G.device) cudaSetDevice(G.device); }
+    tl_error.clear();                      // GrB_*_error / B200_last_error report the failure of the LAST call of this thread
 }
 #define GB_LOCK std::lock_guard<std::recursive_mutex> _lk(G.mu); gb_thread_enter()
 #define GB_CHECK_INIT  do { if (!G.initialized) return gb_fail(GrB_PANIC, nullptr, "GrB_init not called"); } while (0)

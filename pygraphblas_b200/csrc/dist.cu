@@ -7,10 +7,10 @@
 //   * every rank owns one cudaMalloc'd exchange region, exported with cudaIpcGetMemHandle and mapped by all
 //     peers (cudaIpcOpenMemHandle): two replicated-vector buffers (values + presence bytes, double buffered),
 //     one partial buffer, and a page of flags;
-//   * all-gather = ONE push kernel: 128-bit stores of the local slice straight into every rank's replicated
-//     buffer at the slice's offset, __threadfence_system, and the last CTA raises this rank's flag in every
-//     peer; then a one-CTA wait kernel spins (ld.acquire.sys) until every peer's flag shows this step.
-//     No host round trip, no staging copy, no NCCL call on the data path;
+//   * all-gather = a push kernel (128-bit stores of the local slice straight into every rank's replicated
+//     buffer at the slice's offset, system-scope fence) followed by a one-warp signal-and-wait kernel: lane p
+//     raises this rank's flag in rank p (st.release.sys) and spins (ld.acquire.sys) until rank p's flag here
+//     shows this step.  No host round trip, no staging copy, no NCCL call on the data path;
 //   * all-reduce = publish the partial (flag), then every rank folds ITS slice of all ranks' partials with
 //     peer loads in rank order (deterministic, unlike a ring) and pushes the folded slice like the all-gather.
 //
@@ -32,7 +32,6 @@ struct B200_Comm_opaque {
     unsigned char *region = nullptr;                 // this rank's exchange region
     std::vector<unsigned char *> peer;               // every rank's region as mapped here (peer[rank] == region)
     uint64_t step = 0;                               // collectives completed (flag value of the next one = step + 1)
-    unsigned int *done_counter = nullptr;            // last-CTA detection of the push kernels (local)
     GrB_Vector view = nullptr;                       // borrowed view of the current replicated buffer
     bool connected = false;
     std::string err;
@@ -65,15 +64,13 @@ extern "C" GrB_Info B200_Comm_create(B200_Comm *comm, int rank, int world, GrB_I
     cudaError_t e = cudaMalloc((void **)&c->region, c->region_bytes);          // plain cudaMalloc: pool memory cannot be IPC-exported
     if (e != cudaSuccess) { cudaGetLastError(); delete c; return gb_fail(GrB_OUT_OF_MEMORY, nullptr, "B200_Comm_create: cudaMalloc of %zu bytes failed", c->region_bytes); }
     cudaMemsetAsync(c->region, 0, c->region_bytes, G.stream);
-    if (cudaMalloc((void **)&c->done_counter, 256) != cudaSuccess) { cudaGetLastError(); cudaFree(c->region); delete c; return gb_fail(GrB_OUT_OF_MEMORY, nullptr, "B200_Comm_create: out of memory"); }
-    cudaMemsetAsync(c->done_counter, 0, 256, G.stream);
     cudaStreamSynchronize(G.stream);
     c->peer.assign(world, nullptr);
     c->peer[rank] = c->region;
     c->connected = world == 1;
     // the borrowed view handed out by B200_Comm_result
     GrB_Info r = GrB_Vector_new(&c->view, type, n);
-    if (r != GrB_SUCCESS) { cudaFree(c->region); cudaFree(c->done_counter); delete c; return r; }
+    if (r != GrB_SUCCESS) { cudaFree(c->region); delete c; return r; }
     c->view->borrowed = true;
     *comm = c;
     return GrB_SUCCESS;
@@ -111,7 +108,7 @@ extern "C" GrB_Info B200_Comm_free(B200_Comm *comm) {
     if (G.have_device) {
         cudaStreamSynchronize(G.stream);
         for (int p = 0; p < c->world; ++p) if (p != c->rank && c->peer[p]) cudaIpcCloseMemHandle(c->peer[p]);
-        cudaFree(c->region); cudaFree(c->done_counter);
+        cudaFree(c->region);
     }
     if (c->view) { c->view->dval = nullptr; c->view->dpres = nullptr; c->view->dev_valid = false; GrB_Vector_free(&c->view); }
     c->magic = GB_FREED; delete c; *comm = nullptr;
@@ -121,10 +118,12 @@ extern "C" GrB_Info B200_Comm_free(B200_Comm *comm) {
 // ------------------------------------------------------------------ kernels
 struct PeerPtrs { unsigned char *p[MAX_WORLD]; };
 
-// copy `bytes` (multiple of 16) from src to dst[peer] + off for every peer, then the last CTA raises flag[rank] = step on every peer
-__global__ void __launch_bounds__(256) comm_push_kernel(const uint4 *vsrc, size_t vbytes, size_t voff, const uint4 *psrc, size_t pbytes, size_t poff,
-                                                        PeerPtrs dst, int world, int rank, size_t flag_off, int flag_slot,
-                                                        unsigned long long step, unsigned int *done_counter) {
+// copy `bytes` (multiple of 16) from src to dst[peer] + off for every peer.  No flag here: the flags are raised by the NEXT kernel
+// on the stream (comm_signal_wait_kernel) -- a kernel boundary orders this kernel's peer stores before it, and the per-thread
+// system fence below makes that explicit.  (The first version detected its last CTA with one atomic counter: ~600 same-address
+// atomics per push, 10+ us.)
+__global__ void __launch_bounds__(512) comm_push_kernel(const uint4 *vsrc, size_t vbytes, size_t voff, const uint4 *psrc, size_t pbytes, size_t poff,
+                                                        PeerPtrs dst, int world) {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
     const size_t nv = vbytes >> 4, np = pbytes >> 4;
     for (size_t i = tid; i < nv; i += nth) {
@@ -137,33 +136,25 @@ __global__ void __launch_bounds__(256) comm_push_kernel(const uint4 *vsrc, size_
 #pragma unroll 1
         for (int p = 0; p < world; ++p) reinterpret_cast<uint4 *>(dst.p[p] + poff)[i] = v;
     }
-    __threadfence_system();                                   // this thread's peer stores are ordered before what follows
-    __syncthreads();
-    __shared__ bool last;
-    if (threadIdx.x == 0) last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (last) {
-        if (threadIdx.x == 0) *done_counter = 0;              // ready for the next launch
-        __threadfence_system();
-        if ((int)threadIdx.x < world) {
-            unsigned long long *f = reinterpret_cast<unsigned long long *>(dst.p[threadIdx.x] + flag_off) + flag_slot * MAX_WORLD + rank;
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(step) : "memory");
-        }
-    }
+    __threadfence_system();
 }
 
-// one CTA: thread p waits until rank p's flag shows `step`
-__global__ void comm_wait_kernel(const unsigned long long *flags, int world, int flag_slot, unsigned long long step) {
+// one warp: lane p raises this rank's flag (slot, value `step`) in rank p's region, then waits until rank p's flag here shows `step`
+__global__ void comm_signal_wait_kernel(PeerPtrs regions, size_t flag_off, const unsigned long long *my_flags, int world, int rank, int flag_slot,
+                                        unsigned long long step) {
+    __threadfence_system();
     if ((int)threadIdx.x < world) {
-        const unsigned long long *f = flags + flag_slot * MAX_WORLD + threadIdx.x;
+        unsigned long long *f = reinterpret_cast<unsigned long long *>(regions.p[threadIdx.x] + flag_off) + flag_slot * MAX_WORLD + rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(step) : "memory");
+        const unsigned long long *g = my_flags + flag_slot * MAX_WORLD + threadIdx.x;
         unsigned long long v;
         const long long t0 = clock64();
         do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(g) : "memory");
             if (v < step && clock64() - t0 > 40000000000ll) asm volatile("trap;");       // ~20 s: a peer died -- fail loudly instead of hanging the GPU
         } while (v < step);
     }
-    __syncthreads();
+    __syncwarp();
     __threadfence_system();
 }
 
@@ -186,11 +177,18 @@ __global__ void __launch_bounds__(256) comm_fold_kernel(PeerPtrs part, int world
 }
 
 static inline int cgrid(size_t bytes) { return (int)std::max<size_t>(1, std::min<size_t>((bytes / 16 + 255) / 256, (size_t)G.num_sms * 4)); }
+static inline int pgrid(size_t bytes) { return (int)std::max<size_t>(1, std::min<size_t>((bytes / 16 + 511) / 512, (size_t)G.num_sms * 2)); }
 
 static void comm_set_view(B200_Comm c, int which) {
     unsigned char *b = comm_buf(c, c->region, which);
     c->view->dval = b; c->view->dpres = b + c->val_bytes; c->view->dev_valid = true; c->view->dev_nvals = -1; c->view->borrowed = true;
     c->view->host_valid = false; c->view->hi.clear(); c->view->hx.clear(); c->view->pi.clear(); c->view->px.clear();
+}
+
+// flags-only round on slot `slot`: raise mine everywhere, wait for everybody's
+static void comm_signal_wait(B200_Comm c, int slot, unsigned long long step) {
+    PeerPtrs regions{}; for (int p = 0; p < c->world; ++p) regions.p[p] = c->peer[p];
+    comm_signal_wait_kernel<<<1, 32, 0, G.stream>>>(regions, 3 * c->buf_bytes, comm_flags(c, c->region), c->world, c->rank, slot, step); GB_LAUNCHED();
 }
 
 // push (vals, pres) of `len` positions starting at row0 into buffer `which` of every rank, raise flag slot 0, wait for everybody
@@ -199,11 +197,10 @@ static GrB_Info comm_push_and_wait(B200_Comm c, const void *vals, const uint8_t 
     PeerPtrs dst{};
     for (int p = 0; p < c->world; ++p) dst.p[p] = comm_buf(c, c->peer[p], which);
     const size_t vbytes = ((size_t)len * c->esize + 15) & ~(size_t)15, pbytes = ((size_t)len + 15) & ~(size_t)15;
-    const size_t flag_off = (size_t)(3 - which) * c->buf_bytes;           // flags sit after the third buffer, relative to buffer `which`
     const unsigned long long step = c->step + 1;
-    comm_push_kernel<<<cgrid(vbytes + pbytes), 256, 0, G.stream>>>((const uint4 *)vals, vbytes, (size_t)row0 * c->esize, (const uint4 *)pres, pbytes,
-                                                                c->val_bytes + (size_t)row0, dst, c->world, c->rank, flag_off, 0, step, c->done_counter); GB_LAUNCHED();
-    comm_wait_kernel<<<1, 32, 0, G.stream>>>(comm_flags(c, c->region), c->world, 0, step); GB_LAUNCHED();
+    if (len) { comm_push_kernel<<<pgrid(vbytes + pbytes), 512, 0, G.stream>>>((const uint4 *)vals, vbytes, (size_t)row0 * c->esize, (const uint4 *)pres, pbytes,
+                                                                              c->val_bytes + (size_t)row0, dst, c->world); GB_LAUNCHED(); }
+    comm_signal_wait(c, 0, step);
     CU_TRY(cudaGetLastError(), &c->err);
     c->step = step;
     comm_set_view(c, which);
@@ -263,9 +260,7 @@ extern "C" GrB_Info B200_Comm_allreduce(B200_Comm c, const GrB_Vector partial, G
     if (partial->dpres) CU_TRY(cudaMemcpyAsync(mine + c->val_bytes, partial->dpres, (size_t)c->n, cudaMemcpyDeviceToDevice, G.stream), &c->err);
     else { fill_bytes_kernel<<<cgrid(c->n), 256, 0, G.stream>>>(mine + c->val_bytes, (int64_t)c->n, 1); GB_LAUNCHED(); }
     const unsigned long long step = c->step + 1;
-    PeerPtrs regions{}; for (int p = 0; p < c->world; ++p) regions.p[p] = c->peer[p];
-    comm_push_kernel<<<1, 256, 0, G.stream>>>(nullptr, 0, 0, nullptr, 0, 0, regions, c->world, c->rank, 3 * c->buf_bytes, 1, step, c->done_counter); GB_LAUNCHED();
-    comm_wait_kernel<<<1, 32, 0, G.stream>>>(comm_flags(c, c->region), c->world, 1, step); GB_LAUNCHED();
+    comm_signal_wait(c, 1, step);
     // 2. fold my slice of everybody's partial (peer loads, rank order), then push it like an all-gather
     const uint64_t per = ((c->n + (uint64_t)c->world - 1) / c->world + 15) & ~(uint64_t)15;
     const uint64_t e0 = std::min<uint64_t>(c->n, per * (uint64_t)c->rank), e1 = std::min<uint64_t>(c->n, e0 + per);
@@ -307,9 +302,7 @@ extern "C" GrB_Info B200_Comm_barrier(B200_Comm c) {
     GB_LOCK; GB_CHECK_INIT;
     if (!comm_ok(c) || !c->connected) return gb_fail(GrB_INVALID_VALUE, nullptr, "B200_Comm_barrier: not connected");
     const unsigned long long step = c->step + 1;
-    PeerPtrs regions{}; for (int p = 0; p < c->world; ++p) regions.p[p] = c->peer[p];
-    comm_push_kernel<<<1, 256, 0, G.stream>>>(nullptr, 0, 0, nullptr, 0, 0, regions, c->world, c->rank, 3 * c->buf_bytes, 0, step, c->done_counter); GB_LAUNCHED();
-    comm_wait_kernel<<<1, 32, 0, G.stream>>>(comm_flags(c, c->region), c->world, 0, step); GB_LAUNCHED();
+    comm_signal_wait(c, 0, step);
     CU_TRY(cudaGetLastError(), &c->err);
     c->step = step;
     return GrB_SUCCESS;

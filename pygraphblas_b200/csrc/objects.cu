@@ -20,7 +20,6 @@
 
 GBGlobal G;
 thread_local std::string tl_error;
-thread_local int tl_cuda_device = -1;
 
 GrB_Info gb_fail(GrB_Info code, std::string *where, const char *fmt, ...) {
     char buf[1024];
@@ -234,17 +233,37 @@ extern "C" GrB_Info GxB_BinaryOp_ytype(GrB_Type *t, GrB_BinaryOp op) {
     if (!t) return gb_fail(GrB_NULL_POINTER, nullptr, "NULL"); if (!valid_binop(op)) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "bad binaryop");
     *t = op->ytype; return GrB_SUCCESS;
 }
-static GrB_Info monoid_new(GrB_Monoid *m, GrB_BinaryOp op) {
+// A monoid over a builtin operator must be one the kernels know the identity of: the associative, commutative builtin operators.
+// The identity the caller passes has to be that identity (the kernels initialise accumulators from the operator, not from the object).
+static bool op_is_monoid(int opcode, int tc) {
+    switch (opcode) {
+        case OP_MIN: case OP_MAX: case OP_PLUS: case OP_TIMES: case OP_ANY: return true;
+        case OP_LOR: case OP_LAND: case OP_LXOR: case OP_EQ: return tc == TC_BOOL;
+        case OP_BOR: case OP_BAND: case OP_BXOR: case OP_BXNOR: return tc >= TC_UINT8 && tc <= TC_UINT64;
+        default: return false;
+    }
+}
+static GrB_Info monoid_new(GrB_Monoid *m, GrB_BinaryOp op, Sc identity) {
     if (!m) return gb_fail(GrB_NULL_POINTER, nullptr, "GrB_Monoid_new: NULL");
     if (!valid_binop(op)) return gb_fail(GrB_UNINITIALIZED_OBJECT, nullptr, "GrB_Monoid_new: bad operator");
     if (op->xtype != op->ztype || op->ytype != op->ztype) return gb_fail(GrB_DOMAIN_MISMATCH, nullptr, "GrB_Monoid_new: operator domains must all match");
+    if (op->opcode != OP_USER) {
+        const int tc = op->ztype->code;
+        if (!op_is_monoid(op->opcode, tc)) return gb_fail(GrB_DOMAIN_MISMATCH, nullptr, "GrB_Monoid_new: %s is not an associative, commutative builtin operator with an identity", op->name);
+        if (op->opcode != OP_ANY) {
+            const Sc want = sc_monoid_identity(op->opcode, tc);
+            const bool same = tc_is_float(tc) ? (want.d == identity.d) : (want.u == identity.u);
+            if (!same) return gb_fail(GrB_INVALID_VALUE, nullptr, "GrB_Monoid_new: the identity passed is not the identity of %s", op->name);
+        }
+    }
     *m = new GB_Monoid_opaque{GB_MAGIC, op, "user_monoid", false};
     return GrB_SUCCESS;
 }
-#define GB_MONOID_NEW(TN, CT) extern "C" GrB_Info GrB_Monoid_new_##TN(GrB_Monoid *m, GrB_BinaryOp op, CT identity) { (void)identity; return monoid_new(m, op); }
-GB_MONOID_NEW(BOOL, bool) GB_MONOID_NEW(INT8, int8_t) GB_MONOID_NEW(INT16, int16_t) GB_MONOID_NEW(INT32, int32_t)
-GB_MONOID_NEW(INT64, int64_t) GB_MONOID_NEW(UINT8, uint8_t) GB_MONOID_NEW(UINT16, uint16_t) GB_MONOID_NEW(UINT32, uint32_t)
-GB_MONOID_NEW(UINT64, uint64_t) GB_MONOID_NEW(FP32, float) GB_MONOID_NEW(FP64, double)
+#define GB_MONOID_NEW(TN, CT, FIELD) extern "C" GrB_Info GrB_Monoid_new_##TN(GrB_Monoid *m, GrB_BinaryOp op, CT identity) { \
+    Sc s; s.u = 0; s.FIELD = identity; return monoid_new(m, op, s); }
+GB_MONOID_NEW(BOOL, bool, u) GB_MONOID_NEW(INT8, int8_t, i) GB_MONOID_NEW(INT16, int16_t, i) GB_MONOID_NEW(INT32, int32_t, i)
+GB_MONOID_NEW(INT64, int64_t, i) GB_MONOID_NEW(UINT8, uint8_t, u) GB_MONOID_NEW(UINT16, uint16_t, u) GB_MONOID_NEW(UINT32, uint32_t, u)
+GB_MONOID_NEW(UINT64, uint64_t, u) GB_MONOID_NEW(FP32, float, d) GB_MONOID_NEW(FP64, double, d)
 
 extern "C" GrB_Info GrB_Monoid_free(GrB_Monoid *m) {
     if (!m || !*m) return GrB_SUCCESS;

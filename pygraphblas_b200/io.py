@@ -96,3 +96,91 @@ def delimited_read(path, typ, one_based=True, delimiter="\t"):
         raise TypeError("File can contain only 3 columns: row, col and val")
     off = 1 if one_based else 0
     return (data[:, 0].astype(np.int64) - off).astype(np.uint64), (data[:, 1].astype(np.int64) - off).astype(np.uint64), data[:, 2].astype(typ.dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# `.grb` binary files: the LAGraph binwrite layout that suitesparse_graphblas.io.binary reads and writes for the
+# reference (/root/reference/pygraphblas/matrix.py:489-497 binread, :935-942 binwrite; fixture docs/test_binfile.grb).
+# Layout (little endian), reconstructed from the fixture and checked against docs/test_mm.mm, which holds the same matrix:
+#   512-byte text header ("SuiteSparse:GraphBLAS matrix\n<version>\nnrows: ..\nncols: ..\nnvec: ..\nnvals: ..\nformat: ..\nsize: ..\ntype: ..\n")
+#   int32 fmt (0 = by row, 1 = by column), int32 kind (1 hypersparse, 2 sparse, 4 bitmap, 8 full), double hyper_switch,
+#   uint64 nrows, uint64 ncols, int64 nonempty, uint64 nvec, uint64 nvals, int32 typecode, uint64 typesize   (packed)
+#   then, by kind:  Ap[nvec+1] u64 (sparse, hyper) | Ah[nvec] u64 (hyper) | Ab[nrows*ncols] i8 (bitmap) | Ai[nvals] u64 (sparse, hyper)
+#                   | Ax[nvals or nrows*ncols] of the type
+_GRB_TYPECODES = ["BOOL", "INT8", "INT16", "INT32", "INT64", "UINT8", "UINT16", "UINT32", "UINT64", "FP32", "FP64"]
+_GRB_HEADER = 512
+_KIND_NAMES = {1: "HYPER", 2: "SPARSE", 4: "BITMAP", 8: "FULL"}
+
+
+def grb_read(bin_file, opener=None):
+    """-> (I, J, V, nrows, ncols, typ) of a `.grb` file (every storage kind, by row or by column)."""
+    import struct
+    if opener is not None:
+        with opener(bin_file, "rb") as f:
+            data = f.read()
+    elif hasattr(bin_file, "read"):
+        data = bin_file.read()
+    else:
+        with open(bin_file, "rb") as f:
+            data = f.read()
+    if not data.startswith(b"SuiteSparse:GraphBLAS matrix"):
+        raise ValueError("not a SuiteSparse:GraphBLAS binary matrix file")
+    fmt, kind, _hyper, nrows, ncols, _nonempty, nvec, nvals, typecode, typesize = struct.unpack_from("<iidQQqQQiQ", data, _GRB_HEADER)
+    if not 0 <= typecode < len(_GRB_TYPECODES):
+        raise ValueError(f"type code {typecode} is not supported (complex and user-defined types are out of scope)")
+    typ = types.by_name(_GRB_TYPECODES[typecode])
+    if typ.dtype.itemsize != typesize:
+        raise ValueError("type size does not match the type code")
+    off = _GRB_HEADER + struct.calcsize("<iidQQqQQiQ")
+
+    def take(dtype, count):
+        nonlocal off
+        a = np.frombuffer(data, dtype=dtype, count=count, offset=off)
+        off += a.nbytes
+        return a
+
+    vdim, vlen = (nrows, ncols) if fmt == 0 else (ncols, nrows)          # vectors = rows when stored by row
+    if kind in (1, 2):
+        Ap = take("<u8", nvec + 1)
+        Ah = take("<u8", nvec) if kind == 1 else np.arange(nvec, dtype=np.uint64)
+        Ai = take("<u8", nvals)
+        Ax = take(typ.dtype, nvals)
+        major = np.repeat(Ah, np.diff(Ap).astype(np.int64))
+        minor = Ai
+    elif kind == 4:
+        Ab = take("i1", vdim * vlen)
+        Ax = take(typ.dtype, vdim * vlen)
+        pos = np.flatnonzero(Ab)
+        major, minor, Ax = (pos // vlen).astype(np.uint64), (pos % vlen).astype(np.uint64), Ax[pos]
+    elif kind == 8:
+        Ax = take(typ.dtype, vdim * vlen)
+        pos = np.arange(vdim * vlen)
+        major, minor = (pos // vlen).astype(np.uint64), (pos % vlen).astype(np.uint64)
+    else:
+        raise ValueError(f"unknown storage kind {kind}")
+    I, J = (major, minor) if fmt == 0 else (minor, major)
+    return np.ascontiguousarray(I), np.ascontiguousarray(J), np.ascontiguousarray(Ax), int(nrows), int(ncols), typ
+
+
+def grb_write(bin_file, I, J, V, nrows, ncols, typ, comments="", opener=None):
+    """Write tuples as a `.grb` file in the SPARSE, by-row form (entries sorted row-major)."""
+    import struct
+    I = np.asarray(I, dtype=np.uint64); J = np.asarray(J, dtype=np.uint64); V = np.asarray(V, dtype=typ.dtype)
+    order = np.lexsort((J, I))
+    I, J, V = I[order], J[order], V[order]
+    nvals = len(I)
+    Ap = np.zeros(nrows + 1, np.uint64)
+    np.cumsum(np.bincount(I.astype(np.int64), minlength=nrows), out=Ap[1:])
+    head = ("SuiteSparse:GraphBLAS matrix\nv5.1 (libb200grb)\nnrows:  %-18d\nncols:  %-18d\nnvec:   %-18d\nnvals:  %-18d\nformat: SPARSER \n"
+            "size:   %-18d\ntype:   GrB_%-72s\n%s\n" % (nrows, ncols, nrows, nvals, typ.dtype.itemsize, typ.name, comments[:200]))
+    head = head.encode()[:_GRB_HEADER - 2].ljust(_GRB_HEADER - 2, b" ") + b"\n\x00"
+    blob = head + struct.pack("<iidQQqQQiQ", 0, 2, 0.0625, nrows, ncols, -1, nrows, nvals, _GRB_TYPECODES.index(typ.name), typ.dtype.itemsize)
+    blob += Ap.astype("<u8").tobytes() + J.astype("<u8").tobytes() + V.tobytes()
+    if opener is not None:
+        with opener(bin_file, "wb") as f:
+            f.write(blob)
+    elif hasattr(bin_file, "write"):
+        bin_file.write(blob)
+    else:
+        with open(bin_file, "wb") as f:
+            f.write(blob)

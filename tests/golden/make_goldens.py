@@ -134,3 +134,8 @@ known = {
 with open(os.path.join(HERE, "reference_goldens.json"), "w") as f:
     json.dump({"reference": "Graphegon/pygraphblas @ 2d89301", "cases": cases, "known_answers": known}, f, indent=1)
 print(f"wrote {len(cases)} cases")
+
+
+# tests/golden/test_binfile.grb.b64: the reference's binary fixture /root/reference/docs/test_binfile.grb (1021 bytes, the matrix of
+# docs/test_mm.mm in SuiteSparse's BITMAP form), base64-encoded as a golden vector for the `.grb` reader:
+#   python -c "import base64; print(base64.b64encode(open('/root/reference/docs/test_binfile.grb','rb').read()).decode())" > tests/golden/test_binfile.grb.b64

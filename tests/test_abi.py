@@ -164,3 +164,17 @@ def test_calls_from_a_thread_pool():
 
     with ThreadPoolExecutor(8) as ex:
         assert sorted(ex.map(work, range(64))) == list(range(64))
+
+
+def test_monoid_new_checks_operator_and_identity():
+    """A monoid over a builtin operator must be associative / commutative with the identity the kernels use
+    (accumulators are initialised from the operator): MINUS is refused, a wrong identity is refused, the right one accepted."""
+    mon = ffi.new("GrB_Monoid*")
+    assert lib.GrB_Monoid_new_INT64(mon, lib.GrB_PLUS_INT64, 0) == lib.GrB_SUCCESS
+    assert lib.GrB_Monoid_free(mon) == lib.GrB_SUCCESS
+    assert lib.GrB_Monoid_new_FP32(mon, lib.GrB_MIN_FP32, float("inf")) == lib.GrB_SUCCESS
+    assert lib.GrB_Monoid_free(mon) == lib.GrB_SUCCESS
+    assert lib.GrB_Monoid_new_INT64(mon, lib.GrB_MINUS_INT64, 0) == lib.GrB_DOMAIN_MISMATCH
+    assert lib.GrB_Monoid_new_INT64(mon, lib.GrB_PLUS_INT64, 1) == lib.GrB_INVALID_VALUE
+    assert lib.GrB_Monoid_new_INT8(mon, lib.GrB_MAX_INT8, -128) == lib.GrB_SUCCESS
+    assert lib.GrB_Monoid_free(mon) == lib.GrB_SUCCESS
