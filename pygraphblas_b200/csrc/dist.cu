@@ -125,18 +125,27 @@ struct PeerPtrs { unsigned char *p[MAX_WORLD]; };
 __global__ void __launch_bounds__(512) comm_push_kernel(const uint4 *vsrc, size_t vbytes, size_t voff, const uint4 *psrc, size_t pbytes, size_t poff,
                                                         PeerPtrs dst, int world) {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
-    const size_t nv = vbytes >> 4, np = pbytes >> 4;
-    for (size_t i = tid; i < nv; i += nth) {
-        const uint4 v = vsrc[i];
+    // both arrays as one sequence of 16-byte words; four words per thread and trip: the loads are issued together, then the
+    // stores peer by peer (each warp writes 512 contiguous bytes per peer and word)
+    const size_t nv = vbytes >> 4, np = pbytes >> 4, n = nv + np;
+    for (size_t i0 = tid; i0 < n; i0 += 4 * nth) {
+        uint4 v[4]; unsigned char *off[4]; bool ok[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const size_t i = i0 + (size_t)k * nth;
+            ok[k] = i < n;
+            const bool isv = i < nv;
+            off[k] = nullptr;
+            if (ok[k]) { v[k] = isv ? vsrc[i] : psrc[i - nv]; off[k] = reinterpret_cast<unsigned char *>(isv ? voff + (i << 4) : poff + ((i - nv) << 4)); }
+        }
 #pragma unroll 1
-        for (int p = 0; p < world; ++p) reinterpret_cast<uint4 *>(dst.p[p] + voff)[i] = v;
+        for (int p = 0; p < world; ++p) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (ok[k]) *reinterpret_cast<uint4 *>(dst.p[p] + (size_t)off[k]) = v[k];
+        }
     }
-    for (size_t i = tid; i < np; i += nth) {
-        const uint4 v = psrc[i];
-#pragma unroll 1
-        for (int p = 0; p < world; ++p) reinterpret_cast<uint4 *>(dst.p[p] + poff)[i] = v;
-    }
-    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();      // cumulative over the CTA's stores (ordered before it by the barrier)
 }
 
 // one warp: lane p raises this rank's flag (slot, value `step`) in rank p's region, then waits until rank p's flag here shows `step`
@@ -177,7 +186,7 @@ __global__ void __launch_bounds__(256) comm_fold_kernel(PeerPtrs part, int world
 }
 
 static inline int cgrid(size_t bytes) { return (int)std::max<size_t>(1, std::min<size_t>((bytes / 16 + 255) / 256, (size_t)G.num_sms * 4)); }
-static inline int pgrid(size_t bytes) { return (int)std::max<size_t>(1, std::min<size_t>((bytes / 16 + 511) / 512, (size_t)G.num_sms * 2)); }
+static inline int pgrid(size_t bytes) { return (int)std::max<size_t>(1, std::min<size_t>((bytes / 16 + 2047) / 2048, (size_t)G.num_sms * 2)); }
 
 static void comm_set_view(B200_Comm c, int which) {
     unsigned char *b = comm_buf(c, c->region, which);

@@ -43,7 +43,7 @@ static void tunables_load() {
     t.force_push = getenv("B200GRB_FORCE_PUSH") != nullptr; t.spmv_debug = getenv("B200GRB_SPMV_DEBUG") != nullptr;
     t.spmv_pipe = geti("B200GRB_SPMV_PIPE", 0) != 0;
     t.spgemm_trace = getenv("B200GRB_SPGEMM_TRACE") != nullptr;
-    t.stream_blk_log2 = std::min(12, std::max(7, geti("B200GRB_STREAM_BLK", 8)));
+    t.stream_blk_log2 = std::min(12, std::max(7, geti("B200GRB_STREAM_BLK", 7)));
     t.spgemm_v = geti("B200GRB_SPGEMM_V", 0);
     g_tun = t; g_tun_loaded = true;
 }

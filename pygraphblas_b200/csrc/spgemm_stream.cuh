@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(1024, 1) masked_stream_kernel(const StreamArgs
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int bm_shift = 32 - sa.bm_log2;
     const bool exact = sa.exact != 0;
+    const uint32_t item_len = 1u << sa.blk_log2;               // positions of a long B row one work item covers
     const XT *aval = static_cast<const XT *>(p.a_val), *bval = static_cast<const XT *>(p.b_val);
     W *tw = static_cast<W *>(sa.t_words);
     const W ident = pack_slot<ZT>(monoid_identity<ZT>(add));
@@ -161,11 +162,11 @@ __global__ void __launch_bounds__(1024, 1) masked_stream_kernel(const StreamArgs
                 const int nlong = (int)s_nlong;
                 if (tid == 0) {                                   // trips of the long rows, in list order (few rows: serial)
                     uint32_t run = 0;
-                    for (int x = 0; x < nlong; ++x) { const int e = s_long[x]; s_ltrip[x] = run; run += (((s_bs[e] & 3u) + s_len[e]) + 127u) >> 7; }
+                    for (int x = 0; x < nlong; ++x) { const int e = s_long[x]; s_ltrip[x] = run; run += (((s_bs[e] & 3u) + s_len[e]) + item_len - 1u) >> sa.blk_log2; }
                     s_ltrips = run;
                 }
                 __syncthreads();
-                // ---- work items of a warp: item < nent = the whole (short) B row of entry `item`; item >= nent = ONE 128-position trip
+                // ---- work items of a warp: item < nent = the whole (short) B row of entry `item`; item >= nent = one piece (1 << blk_log2 positions)
                 //      of a long row.  One streaming loop serves both.
                 const uint32_t nitems = (uint32_t)nent + s_ltrips;
                 int lx = 0;                                        // cursor into the long-row list (items come in increasing order)
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(1024, 1) masked_stream_kernel(const StreamArgs
                             while (lx + 1 < nlong && s_ltrip[lx + 1] <= t) ++lx;
                             ent = s_long[lx];
                             const uint32_t b0 = s_bs[ent], p0 = b0 & ~3u, k = t - s_ltrip[lx];
-                            s = max(b0, p0 + k * 128u); e = min(b0 + s_len[ent], p0 + (k + 1u) * 128u);
+                            s = max(b0, p0 + k * item_len); e = min(b0 + s_len[ent], p0 + (k + 1u) * item_len);
                         }
                     }
                     // ---- stream positions [s, e): trips of 128 (four consecutive ids per lane, one 128-bit load); the next trip's load is
@@ -197,8 +198,13 @@ __global__ void __launch_bounds__(1024, 1) masked_stream_kernel(const StreamArgs
                         if (pbn < e) cn = __ldg(reinterpret_cast<const uint4 *>(p.b_col + pbn));
                         const uint32_t jj[4] = {c.x, c.y, c.z, c.w};
                         bool h[4];
+                        const bool whole = tb >= s && tb + 128u <= e;          // warp-uniform: every position of the trip is inside [s, e)
 #pragma unroll
-                        for (uint32_t i = 0; i < 4; ++i) { const uint32_t b = bit_of(jj[i]); h[i] = ((bm[b >> 5] >> (b & 31u)) & 1u) && pb + i >= s && pb + i < e; }
+                        for (uint32_t i = 0; i < 4; ++i) {
+                            const uint32_t b = bit_of(jj[i]);
+                            h[i] = (bm[b >> 5] >> (b & 31u)) & 1u;
+                            if (!whole) h[i] = h[i] && pb + i >= s && pb + i < e;
+                        }
 #pragma unroll
                         for (uint32_t i = 0; i < 4; ++i) {
                             const uint32_t ball = __ballot_sync(0xffffffffu, h[i]);
