@@ -198,13 +198,8 @@ __global__ void __launch_bounds__(1024, 1) masked_stream_kernel(const StreamArgs
                         if (pbn < e) cn = __ldg(reinterpret_cast<const uint4 *>(p.b_col + pbn));
                         const uint32_t jj[4] = {c.x, c.y, c.z, c.w};
                         bool h[4];
-                        const bool whole = tb >= s && tb + 128u <= e;          // warp-uniform: every position of the trip is inside [s, e)
 #pragma unroll
-                        for (uint32_t i = 0; i < 4; ++i) {
-                            const uint32_t b = bit_of(jj[i]);
-                            h[i] = (bm[b >> 5] >> (b & 31u)) & 1u;
-                            if (!whole) h[i] = h[i] && pb + i >= s && pb + i < e;
-                        }
+                        for (uint32_t i = 0; i < 4; ++i) { const uint32_t b = bit_of(jj[i]); h[i] = ((bm[b >> 5] >> (b & 31u)) & 1u) && pb + i >= s && pb + i < e; }
 #pragma unroll
                         for (uint32_t i = 0; i < 4; ++i) {
                             const uint32_t ball = __ballot_sync(0xffffffffu, h[i]);

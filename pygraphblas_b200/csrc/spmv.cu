@@ -415,9 +415,16 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
 
     const int64_t n = (int64_t)out_n;
     const size_t zsz = (size_t)tc_size(zt);
+    // T's buffers become w (no mask, no accumulator: w<-T).  When w already owns device buffers of the right shape and is not an
+    // operand of this call, T is formed in place -- the iterated call `A.mxv(u, out=w)` then allocates nothing.
     void *tval = nullptr; uint8_t *tpres = nullptr;
-    GB_TRY(dmalloc(&tval, (size_t)n * zsz + 16, err));
-    GB_TRY(dmalloc((void **)&tpres, (size_t)n + 16, err));
+    const bool in_place = !need_final && w != u && w->dev_valid && w->dval && w->dpres && w->type->code == zt && !w->borrowed &&
+                          !w->h2d_pending && !w->d2h_pending && a_cast != w->dval && u_cast != w->dval;
+    if (in_place) { tval = w->dval; tpres = w->dpres; }
+    else {
+        GB_TRY(dmalloc(&tval, (size_t)n * zsz + 16, err));
+        GB_TRY(dmalloc((void **)&tpres, (size_t)n + 16, err));
+    }
 
     // mask + saturating monoid (BFS-shaped): skip masked-out rows, stop rows at the first hit
     const bool use_pull = mask != nullptr && (add == OP_LOR || add == OP_LAND || add == OP_ANY) && c.nnz > 0 && !tn.no_pull;
@@ -446,7 +453,7 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
         CU_TRY(cudaMemsetAsync(pa.long_count, 0, sizeof(int), G.stream), err);
         GrB_Info r = pushed ? GrB_SUCCESS : spmv_masked_pull_dispatch(xt, zt, pa, err);
         dfree(pa.long_rows); dfree(pa.long_count);
-        if (r != GrB_SUCCESS) { dfree(tval); dfree(tpres); dfree(a_cast); dfree(u_cast); return r; }
+        if (r != GrB_SUCCESS) { if (!in_place) { dfree(tval); dfree(tpres); } dfree(a_cast); dfree(u_cast); return r; }
     }
     // dense u + specialised semiring: warp-independent run kernel on the cached run plan
     const bool run_ok = !use_pull && (fast_sr || xt == zt || zt == TC_BOOL);     // specialised or run-time operators; dense or sparse u
@@ -484,7 +491,7 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
             kernel_name = sparse_u ? "run (sparse u)" : "run";
         }
         const bool ok = fast_sr ? spmv_run_dispatch(xt, add, kmul, ra, hot_kb > 0 ? &hot : nullptr, (size_t)hot_kb << 10) : spmv_run_generic(xt, zt, ra);
-        if (!ok) { dfree(tval); dfree(tpres); dfree(a_cast); dfree(u_cast); return gb_fail(GrB_PANIC, err, "mxv: internal dispatch error"); }
+        if (!ok) { if (!in_place) { dfree(tval); dfree(tpres); } dfree(a_cast); dfree(u_cast); return gb_fail(GrB_PANIC, err, "mxv: internal dispatch error"); }
     } else if (c.nnz == 0) {
         clear_presence_kernel<<<grid_for(n), 256, 0, G.stream>>>(tpres, n); GB_LAUNCHED();
         kernel_name = "empty";
@@ -509,12 +516,17 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
             dfree(a.dbg);
         }
         dfree(a.head_val); dfree(a.tail_val); dfree(a.head_has); dfree(a.tail_has); dfree(a.tail_row);
-        if (r != GrB_SUCCESS) { dfree(tval); dfree(tpres); dfree(a_cast); dfree(u_cast); return r; }
+        if (r != GrB_SUCCESS) { if (!in_place) { dfree(tval); dfree(tpres); } dfree(a_cast); dfree(u_cast); return r; }
     }
     if (burble.on) burble.note(kernel_name, (double)c.nnz * (4.0 + (need_a ? tc_size(xt) : 0)) + (double)(c.nrows + 1) * 4 + (double)c.ncols * (need_u ? tc_size(xt) : 0) + (double)n * (zsz + 1));
     dfree(a_cast); dfree(u_cast);
     vector_mark_used(u); if (mask) vector_mark_used(mask);          // an overlapped import into u may start as soon as these kernels are done
 
+    if (in_place) {                    // T was formed in w's own buffers: only the bookkeeping changes
+        w->dev_nvals = -1; w->host_valid = false; w->hi.clear(); w->hx.clear(); w->pi.clear(); w->px.clear();
+        CU_TRY(cudaGetLastError(), err);
+        return GrB_SUCCESS;
+    }
     // ---- w<mask> = accum(w, t)   (vector_ops.cu)
     return vector_write(w, mask, accum, f, tval, tpres, zt, /*t_scalar=*/false, /*region=*/nullptr, /*own_t=*/true);
 }

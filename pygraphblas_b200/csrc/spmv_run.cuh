@@ -310,8 +310,8 @@ __global__ void __launch_bounds__(256) spmv_run_fixup_kernel(const RunArgs p) {
 
 // shared memory the hot-table kernel can use for its table, after the warp stages and barriers
 template <typename XT> static inline uint32_t hot2_table_entries(bool need_a, uint32_t henc, size_t limit_bytes) {
-    int max_optin = 0;
-    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, G.device);
+    static int max_optin = 0;                   // one device per process: ask once
+    if (!max_optin) cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, G.device);
     const size_t fixed = (size_t)HOT2_WARPS * hot2_stage_bytes<XT>(need_a) + (HOT2_WARPS + 1) * 8 + 8;
     size_t avail = (size_t)max_optin > fixed + 256 ? (size_t)max_optin - fixed - 256 : 0;
     avail = std::min(avail, limit_bytes);
@@ -327,13 +327,17 @@ static void spmv_run_launch(const RunArgs &a, const Hot2Args *hot, size_t table_
             h.tab_n = hot2_table_entries<XT>(NEED_A, h.henc, table_limit);
             const size_t smem = (size_t)HOT2_WARPS * hot2_stage_bytes<XT>(NEED_A) + (HOT2_WARPS + 1) * 8 + 8 + (size_t)h.tab_n * sizeof(XT);
             const int ctas = (int)std::min<int64_t>(G.num_sms, ceil_div(a.nruns, HOT2_WARPS));
+            // the dynamic shared-memory limit of a kernel is raised once per size (a driver call per launch is host time the
+            // multi-GPU step cannot hide: its kernels take tens of microseconds)
             if (sizeof(XT) <= 4 && tunables().spmv_pipe) {
                 auto kernel = spmv_run_hot2_kernel<XT, ZT, ADD, MUL, true>;
-                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                static size_t set_for = 0;
+                if (set_for != smem) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set_for = smem; }
                 kernel<<<ctas, HOT2_WARPS * 32, smem, G.stream>>>(a, h); GB_LAUNCHED();
             } else {
                 auto kernel = spmv_run_hot2_kernel<XT, ZT, ADD, MUL, false>;
-                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                static size_t set_for = 0;
+                if (set_for != smem) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set_for = smem; }
                 kernel<<<ctas, HOT2_WARPS * 32, smem, G.stream>>>(a, h); GB_LAUNCHED();
             }
             spmv_run_fixup_kernel<ZT, ADD, false><<<(unsigned)ceil_div(a.nruns * 8, 256), 256, 0, G.stream>>>(a); GB_LAUNCHED();
