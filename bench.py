@@ -434,7 +434,8 @@ def run_b200(args):
     extras = []
     if not args.no_extras:
         if world == 1:
-            extras = [("spgemm", bench_spgemm), ("spgemm_unmasked", bench_spgemm_unmasked), ("bfs", bench_bfs), ("sssp", bench_sssp)]
+            extras = [("spgemm", bench_spgemm), ("spgemm_unmasked", bench_spgemm_unmasked), ("spgemm_unmasked_streamed", bench_spgemm_unmasked_streamed),
+                      ("bfs", bench_bfs), ("sssp", bench_sssp)]
         else:
             extras = [("spgemm", bench_spgemm_panels), ("bfs", bench_bfs_dist), ("sssp", bench_sssp_dist)]
     for key, fn in extras:
@@ -546,6 +547,17 @@ def bench_e2e(ctx, A_mirror, n, lrows, nnz, u_host, x_dev):
            "serial": {"value": nnz / serial_s / 1e9, "ms_per_step": serial_s * 1e3, "what": "the same step with blocking copies, one step at a time (latency-bound)"}}
     same = all(np.array_equal(w_pin[b][p_pin[b] != 0], w_serial[p_serial != 0]) and np.array_equal(p_pin[b], p_serial) for b in range(NB))
     res["pipelined_equals_serial"] = bool(same)
+    if not same:                                     # reported, not hidden: which buffers differ, where and by how much
+        diag = []
+        for b in range(NB):
+            dp = np.flatnonzero(p_pin[b] != p_serial)
+            both = (p_pin[b] != 0) & (p_serial != 0)
+            dv = np.flatnonzero(both & (w_pin[b] != w_serial))
+            rel = np.abs(w_pin[b][dv].astype(np.float64) - w_serial[dv]) / np.maximum(np.abs(w_serial[dv].astype(np.float64)), 1e-30) if len(dv) else np.zeros(0)
+            diag.append({"buffer": b, "presence_diffs": int(len(dp)), "value_diffs": int(len(dv)), "first_value_diffs": [int(x) for x in dv[:4]],
+                         "max_rel_diff": float(rel.max()) if len(dv) else 0.0,
+                         "zeros_where_serial_nonzero": int(np.count_nonzero(both & (w_pin[b] == 0) & (w_serial != 0)))})
+        res["mismatch"] = diag
     if x_dev is not None:
         res["matches_device_result"] = bool(same and np.array_equal(w_serial[p_serial != 0], x_dev[p_serial != 0]))
     del keep
@@ -681,6 +693,105 @@ def bench_spgemm_unmasked(ctx, *_):
     res["parity_full_size"] = bool(np.array_equal(Cp[:rows + 1], R.indptr) and np.array_equal(Cj[:k1], R.indices) and np.array_equal(Cx[:k1], R.data))
     res["parity_what"] = f"pattern and values of the first {rows} rows against scipy (exact: quarter-valued inputs)"
     del Ssub
+    return res
+
+
+def streamed_plan(n, indptr, indices, vals, cap):
+    """Row panels of the streamed unmasked product: greedy cuts so that a panel holds at most `cap` products (at least one row),
+    the total number of products, and the closed form of the sum of all values of C = A (+.second) A:
+    sum_i sum_{k in A(i,:)} rowsum_A(k)  (fp64; exact for quarter-valued entries)."""
+    rowlen = np.diff(indptr)
+    rows = np.repeat(np.arange(n), rowlen)
+    fl = np.bincount(rows, weights=rowlen[indices].astype(np.float64), minlength=n)          # products of row i
+    cum = np.concatenate(([0.0], np.cumsum(fl)))
+    cuts = [0]
+    while cuts[-1] < n:
+        r0 = cuts[-1]
+        r1 = int(np.searchsorted(cum, cum[r0] + cap, side="right")) - 1
+        cuts.append(min(n, max(r1, r0 + 1)))
+    rowsum = np.bincount(rows, weights=np.asarray(vals, np.float64), minlength=n)
+    return cuts, int(cum[-1]), float(rowsum[indices].sum())
+
+
+def streamed_sample(n, indptr):
+    """A strided sample of rows (R-MAT hubs sit at low ids: the stride mixes heavy and light rows): the row ids, the sample's
+    row pointer and the positions of its entries in the parent CSR."""
+    S = np.arange(min(7, n - 1), n, max(1, n // 1024))
+    sp_ptr = np.concatenate(([0], np.cumsum(np.diff(indptr)[S]))).astype(np.int64)
+    take = np.concatenate([np.arange(indptr[r], indptr[r + 1]) for r in S]).astype(np.int64)
+    return S, sp_ptr, take
+
+
+def bench_spgemm_unmasked_streamed(ctx, *_):
+    """configs[3]'s product WITHOUT the mask at configs[3]'s own scale: A (+.second) A on R-MAT scale 20 makes ~2e10 products and
+    ~9e9 output entries -- 72 GB as CSR and more entries than 32-bit offsets address -- so it is STREAMED as row panels
+    C_g = A_g (+.second) A (A_g = a block of rows of A, blocks cut by products): each panel is formed by GrB_mxm (symbolic ->
+    numeric), reduced on the device to (nvals, sum of values) and dropped before the next one.  Parity: the sum of all values of
+    C against its closed form sum_i sum_{k in A(i,:)} rowsum_A(k) (exact: quarter-valued inputs, fp64 reductions), and pattern +
+    values of a strided sample of rows against scipy."""
+    torch, gb, args, stream = ctx["torch"], ctx["gb"], ctx["args"], ctx["stream"]
+    from pygraphblas_b200 import Matrix, FP32
+    import scipy.sparse as sp
+    lib = gb.lib
+    scale = args.spgemm_streamed_scale
+    n, indptr, indices = cached_graph(scale)
+    nnz = len(indices)
+    rng = np.random.default_rng(5)
+    vals = (rng.integers(1, 5, nnz) / 4.0).astype(np.float32)
+    cap = float(args.spgemm_streamed_cap)
+    cuts, total_products, expect = streamed_plan(n, indptr, indices, vals, cap)
+    A = Matrix.from_csr(indptr, indices, vals, n, n, FP32)
+    panels = []
+    for g in range(len(cuts) - 1):
+        r0, r1 = cuts[g], cuts[g + 1]
+        k0, k1 = int(indptr[r0]), int(indptr[r1])
+        panels.append(Matrix.from_csr((indptr[r0:r1 + 1] - k0).astype(np.int64), indices[k0:k1], vals[k0:k1], r1 - r0, n, FP32))
+
+    def sweep():
+        nv, total, prods = 0, 0.0, 0
+        flops, nout = gb.ffi.new("uint64_t*"), gb.ffi.new("uint64_t*")
+        for Ag in panels:
+            C = Ag.mxm(A, semiring=FP32.PLUS_SECOND)
+            lib.B200_last_mxm_stats(flops, nout)
+            nv += int(C.nvals); prods += int(flops[0])
+            total += float(C.reduce_float())                  # FP64 PLUS monoid: exact for these values
+            C = None                                          # the panel goes back to the pool before the next one is formed
+        return nv, total, prods
+
+    sweep()                                                   # grows the memory pool to the largest panel
+    lib.B200_device_synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    nout, total, prods = sweep()
+    e1.record(stream)
+    lib.B200_device_synchronize(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    alg = spgemm_alg_bytes(nnz, prods, nout, n, 0, 0, 4, 4)
+    peak, _ = measured_peaks()
+    res = {"workload": f"R-MAT scale-{scale}: C = A (+.second) A, FP32, unmasked, streamed as {len(panels)} row panels of <= {cap:.3g} products "
+                       "(BASELINE.json configs[3] product without the mask, at configs[3]'s scale)",
+           "value": nout / (ms * 1e-3) / 1e6, "unit": "Mnnz-out/s", "ms": ms, "panels": len(panels), "nnz_A": nnz, "products": prods, "nnz_out": nout,
+           "gproducts_per_s": prods / (ms * 1e-3) / 1e9, "csr_bytes_of_C": int(nout) * 8,
+           "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                        "algorithmic_bytes": int(alg), "traffic": None},
+           "timed": "per panel: GrB_mxm (flops, bins, symbolic, scan, numeric), nvals, GrB_Matrix_reduce_FP64; the panels' results are dropped, not kept"}
+    # a strided sample of rows (hubs sit at low ids: the stride mixes heavy and light rows) against scipy, single thread
+    S, sp_ptr, take = streamed_sample(n, indptr)
+    As = Matrix.from_csr(sp_ptr, indices[take], vals[take], len(S), n, FP32)
+    Cs = As.mxm(A, semiring=FP32.PLUS_SECOND)
+    Cp, Cj, Cx = Cs.to_csr()
+    full = sp.csr_matrix((vals, indices, indptr), shape=(n, n))
+    ones_s = sp.csr_matrix((np.ones(len(take), np.float32), indices[take], sp_ptr), shape=(len(S), n))
+    t0 = time.perf_counter()
+    R = (ones_s @ full).tocsr()
+    cpu_s = time.perf_counter() - t0
+    R.sort_indices()
+    res["cpu_baseline"] = {"value": R.nnz / cpu_s / 1e6, "unit": "Mnnz-out/s", "cores": 1, "kind": "port",
+                           "sample": f"{len(S)} rows (every {max(1, n // 1024)}th) of the same product ({R.nnz} output entries) with scipy.sparse csr_matmat, 1 thread"}
+    sample_ok = bool(np.array_equal(Cp, R.indptr) and np.array_equal(Cj, R.indices) and np.array_equal(Cx, R.data))
+    res["sum_of_values"] = total; res["sum_of_values_closed_form"] = expect
+    res["parity_full_size"] = bool(sample_ok and total == expect and prods == total_products)
+    res["parity_what"] = (f"sum of all {nout} values of C == its closed form (exact), products == sum of row flops, and pattern + values of {len(S)} sampled rows against scipy")
     return res
 
 
@@ -980,6 +1091,8 @@ def main():
     ap.add_argument("--scale", type=int, default=22)
     ap.add_argument("--spgemm-scale", type=int, default=20)
     ap.add_argument("--spgemm-unmasked-scale", type=int, default=17)
+    ap.add_argument("--spgemm-streamed-scale", type=int, default=20)
+    ap.add_argument("--spgemm-streamed-cap", type=float, default=1.5e9, help="products per row panel of the streamed unmasked SpGEMM")
     ap.add_argument("--no-extras", "--no-spgemm", dest="no_extras", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--quick", action="store_true", help="timed SpMV loop only (for ncu): no e2e / CPU baseline / extras")

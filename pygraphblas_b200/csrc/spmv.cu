@@ -418,8 +418,13 @@ static GrB_Info mxv_core(GrB_Vector w, const GrB_Vector mask, const GrB_BinaryOp
     // T's buffers become w (no mask, no accumulator: w<-T).  When w already owns device buffers of the right shape and is not an
     // operand of this call, T is formed in place -- the iterated call `A.mxv(u, out=w)` then allocates nothing.
     void *tval = nullptr; uint8_t *tpres = nullptr;
-    const bool in_place = !need_final && w != u && w->dev_valid && w->dval && w->dpres && w->type->code == zt && !w->borrowed &&
-                          !w->h2d_pending && !w->d2h_pending && a_cast != w->dval && u_cast != w->dval;
+    const bool w_reusable = !need_final && w != u && w->dev_valid && w->dval && w->dpres && w->type->code == zt && !w->borrowed &&
+                            a_cast != w->dval && u_cast != w->dval;
+    const bool in_place = w_reusable && (tn.mxv_inplace == 2 || (tn.mxv_inplace == 1 && !w->h2d_pending && !w->d2h_pending));
+    if (in_place && tn.mxv_inplace == 2) {      // whatever the flags say: the kernels below start after w's last overlapped copies
+        if (w->ev_h2d) { cudaStreamWaitEvent(G.stream, w->ev_h2d, 0); cudaStreamWaitEvent(G.stream, w->ev_d2h, 0); }
+        w->h2d_pending = false; w->d2h_pending = false;
+    }
     if (in_place) { tval = w->dval; tpres = w->dpres; }
     else {
         GB_TRY(dmalloc(&tval, (size_t)n * zsz + 16, err));

@@ -245,9 +245,6 @@ __global__ void __launch_bounds__(HOT2_WARPS * 32, 1) spmv_run_hot2_kernel(const
         const int64_t q = r * RUN + lane * 8;
         const int nvalid = (int)min((int64_t)8, max((int64_t)0, p.nnz - q));
         uint32_t c[8];
-        const uint4 *sc = reinterpret_cast<const uint4 *>(stage) + lane * 2;
-        const uint4 c0 = sc[0], c1 = sc[1];
-        c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
         if (NEED_A) {
             const XT *sa = reinterpret_cast<const XT *>(stage + RUN * 4) + lane * 8;
             if constexpr (sizeof(XT) == 4) {
@@ -260,12 +257,27 @@ __global__ void __launch_bounds__(HOT2_WARPS * 32, 1) spmv_run_hot2_kernel(const
                 for (int j = 0; j < 8; ++j) L.a[j] = sa[j];
             }
         }
+        const uint4 *sc = reinterpret_cast<const uint4 *>(stage) + lane * 2;
+        const uint4 c0 = sc[0], c1 = sc[1];
+        c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+        // WAR guard of the stage.  The bulk copy of the next run writes this stage through the async proxy; nothing orders it
+        // after generic-proxy loads that were only ISSUED (a __syncwarp does not wait for their data), and under load a
+        // shared-memory load can sit in the LSU queue longer than an L2-hit bulk copy takes -- a lane then folds words of the
+        // NEXT run into this run's rows (seen as one wrong hub-row sum in ~1 % of the launches of the overlapped e2e loop).  A vote
+        // that READS the first and last loaded word of every lane cannot issue before the warp's loads have written their
+        // registers; its predicate is never true (encoded ids stay below 2^32 - 1: spmv_hot_plan), so the copy is always issued.
+        uint32_t guard = c[0] & c[7];
+        if (NEED_A) {                                                       // the value loads take part too (first and last word of the lane)
+            uint32_t w0, w7;
+            memcpy(&w0, &L.a[0], 4); memcpy(&w7, &L.a[7], 4);
+            guard &= (w0 | 0x80000000u) & (w7 | 0x80000000u);
+        }
+        const unsigned never = __ballot_sync(0xffffffffu, guard == 0xFFFFFFFFu);
         if (nvalid < 8) {                                                   // tail of the last run: what lies past nnz is not data
 #pragma unroll
             for (int j = 0; j < 8; ++j) { if (j >= nvalid) { c[j] = henc; if (NEED_A) L.a[j] = (XT)1; } }
         }
-        __syncwarp();                                                       // every lane has its words: the stage is free
-        if (lane == 0 && r + stride < p.nruns) issue(r + stride);
+        if (lane == 0 && never == 0u && r + stride < p.nruns) issue(r + stride);
         spmv_run_gather<XT, MUL, false>(p, r, lane, nvalid, c, L, gather);
     };
     if constexpr (sizeof(XT) > 4 || !PIPE) {
