@@ -166,6 +166,7 @@ struct Tunables {
     bool spgemm_trace = false; // B200GRB_SPGEMM_TRACE phase times of GrB_mxm (masked) on stderr
     int stream_blk_log2 = 7;   // B200GRB_STREAM_BLK   log2 of the block of a long B row one warp takes (masked SpGEMM)
     int spgemm_v = 0;          // B200GRB_SPGEMM_V     masked SpGEMM kernel generation (0 = default)
+    bool spgemm_esc = true;    // B200GRB_SPGEMM_ESC   0: the shared-memory bins of the unmasked numeric pass use the hash kernels instead of expand-sort-compress
     int mxv_inplace = 1;       // B200GRB_MXV_INPLACE  0: mxv / vxm never form T in w's own buffers; 1: when w has no copy in flight;
                                //                      2: always, the compute stream first joins w's last overlapped copies
 };

@@ -46,6 +46,7 @@ static void tunables_load() {
     t.stream_blk_log2 = std::min(12, std::max(7, geti("B200GRB_STREAM_BLK", 7)));
     t.spgemm_v = geti("B200GRB_SPGEMM_V", 0);
     t.mxv_inplace = geti("B200GRB_MXV_INPLACE", 1);
+    t.spgemm_esc = geti("B200GRB_SPGEMM_ESC", 1) != 0;
     g_tun = t; g_tun_loaded = true;
 }
 const Tunables &tunables() { if (!g_tun_loaded) tunables_load(); return g_tun; }

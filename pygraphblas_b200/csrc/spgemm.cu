@@ -306,6 +306,135 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *s_warp, int *tot
     return r;
 }
 
+// ------------------------------------------------------------------ unmasked, numeric pass: expand - sort - compress (ESC)
+// The numeric pass of the two shared-memory bins without a hash table.  The products of a row are EXPANDED into shared memory in
+// their Gustavson order (key = column << 32 | position, the value stays at its position), the keys are SORTED by a bitonic
+// network over the next power of two of the row's OWN product count (the hash path sorts its whole table -- 256 or 4096 slots --
+// whatever the row holds), and equal columns are COMPRESSED by folding their values in position order.  No atomics and no table
+// to clear; a floating-point PLUS monoid gives the same bit pattern on every run (the hash path adds in arrival order).  One
+// warp per row of the small bin (<= 128 products), one CTA per row of the medium bin (<= 2048).  The row's output count comes
+// from the symbolic pass (c_ptr), as for the hash kernels.
+static constexpr int ESC_SMALL = 128, ESC_MEDIUM = 2048;
+static constexpr size_t ESC_SMEM_SMALL = (size_t)8 * ESC_SMALL * 16;                       // 8 warps x (keys 8 B + value words 8 B)
+static constexpr size_t ESC_SMEM_MEDIUM = (size_t)ESC_MEDIUM * 16 + 3 * 256 * 4 + 256 * 8;   // + offsets, starts, lengths, A values of a chunk
+
+template <typename XT, typename ZT, int ADD, int MUL, bool WARP>
+__global__ void __launch_bounds__(256) esc_numeric_kernel(const GemmArgs p) {
+    typedef typename SlotWord<ZT>::W W;
+    constexpr int CAP = WARP ? ESC_SMALL : ESC_MEDIUM;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ int s_warp[33];
+    const int add = ADD >= 0 ? ADD : p.add_op;
+    const int mul = MUL >= 0 ? MUL : p.mul_op;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int groups = WARP ? nwarps : 1, gid = WARP ? warp : 0;
+    const int tid = WARP ? lane : (int)threadIdx.x, gsize = WARP ? 32 : (int)blockDim.x;
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw) + (size_t)gid * CAP;
+    W *vals = reinterpret_cast<W *>(smem_raw + (size_t)groups * CAP * 8) + (size_t)gid * CAP;
+    const int64_t idx = (int64_t)blockIdx.x * groups + gid;
+    if (idx >= p.nbin) return;                  // a whole warp (WARP) or never (one CTA per row): no CTA barrier is skipped
+    const int64_t row = p.rows[idx];
+    const uint32_t as = p.a_ptr[row], ae = p.a_ptr[row + 1];
+    const XT *aval = static_cast<const XT *>(p.a_val), *bval = static_cast<const XT *>(p.b_val);
+    int F = 0;                                  // products expanded so far (uniform over the group)
+
+    // ---- expand
+    if constexpr (WARP) {
+        for (uint32_t pa0 = as; pa0 < ae; pa0 += 32) {          // a lane per A entry, each lane walks its B row
+            const uint32_t pa = pa0 + lane;
+            uint32_t bs = 0, len = 0; XT av = (XT)1;
+            if (pa < ae) {
+                const uint32_t k = p.a_col[pa];
+                bs = p.b_ptr[k]; len = p.b_ptr[k + 1] - bs;
+                if (p.need_a) av = gload<XT>(aval + pa);
+            }
+            int inc = (int)len;
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+            const int off = F + inc - (int)len;
+            for (uint32_t t = 0; t < len; ++t) {
+                const int pos = off + (int)t;
+                if (pos < CAP) {
+                    const uint32_t j = __ldg(p.b_col + bs + t);
+                    const XT bv = p.need_b ? gload<XT>(bval + bs + t) : (XT)1;
+                    keys[pos] = ((unsigned long long)j << 32) | (unsigned)pos;
+                    vals[pos] = pack_slot<ZT>(MulApply<XT, ZT>::f(mul, av, bv));
+                }
+            }
+            F += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    } else {
+        uint32_t *s_off = reinterpret_cast<uint32_t *>(smem_raw + (size_t)CAP * 16);
+        uint32_t *s_bs = s_off + 256, *s_len = s_bs + 256;
+        XT *s_av = reinterpret_cast<XT *>(s_len + 256);
+        for (uint32_t pa0 = as; pa0 < ae; pa0 += 256) {         // a thread per A entry of the chunk, then a warp per entry, lanes along its B row
+            const uint32_t pa = pa0 + threadIdx.x;
+            uint32_t bs = 0, len = 0; XT av = (XT)1;
+            if (pa < ae) {
+                const uint32_t k = p.a_col[pa];
+                bs = p.b_ptr[k]; len = p.b_ptr[k + 1] - bs;
+                if (p.need_a) av = gload<XT>(aval + pa);
+            }
+            int total = 0;
+            const int off = block_exclusive_scan((int)len, s_warp, &total);
+            s_off[threadIdx.x] = (uint32_t)(F + off); s_bs[threadIdx.x] = bs; s_len[threadIdx.x] = len; s_av[threadIdx.x] = av;
+            __syncthreads();
+            const int nent = (int)min(256u, ae - pa0);
+            for (int e = warp; e < nent; e += nwarps) {
+                const uint32_t o = s_off[e], b0 = s_bs[e], l = s_len[e];
+                const XT a = s_av[e];
+                for (uint32_t t = lane; t < l; t += 32) {
+                    const uint32_t pos = o + t;
+                    if (pos < (uint32_t)CAP) {
+                        const uint32_t j = __ldg(p.b_col + b0 + t);
+                        const XT bv = p.need_b ? gload<XT>(bval + b0 + t) : (XT)1;
+                        keys[pos] = ((unsigned long long)j << 32) | pos;
+                        vals[pos] = pack_slot<ZT>(MulApply<XT, ZT>::f(mul, a, bv));
+                    }
+                }
+            }
+            F += total;
+            __syncthreads();
+        }
+    }
+    if (F > CAP) F = CAP;                       // cannot happen: the bins are cut by the row's product count
+
+    // ---- sort the keys (padding sorts last)
+    int n2 = 2;
+    while (n2 < F) n2 <<= 1;
+    for (int s = F + tid; s < n2; s += gsize) keys[s] = ~0ull;
+    group_sync<WARP>();
+    bitonic_sort_u64<WARP>(keys, n2, tid, gsize);
+
+    // ---- compress: the first key of every column folds the values of its run, in position order
+    const int64_t base = p.c_ptr[row];
+    ZT *cval = static_cast<ZT *>(p.c_val);
+    int cnt = 0;
+    for (int i0 = 0; i0 < F; i0 += gsize) {
+        const int i = i0 + tid;
+        const bool valid = i < F;
+        const unsigned long long e = valid ? keys[i] : 0ull;
+        const uint32_t col = (uint32_t)(e >> 32);
+        const bool head = valid && (i == 0 || (uint32_t)(keys[i - 1] >> 32) != col);
+        int rank = 0, total = 0;
+        if constexpr (WARP) {
+            const unsigned m = __ballot_sync(0xffffffffu, head);
+            rank = cnt + __popc(m & ((1u << lane) - 1u)); total = __popc(m);
+        } else {
+            rank = cnt + block_exclusive_scan(head ? 1 : 0, s_warp, &total);
+        }
+        if (head) {
+            ZT acc = unpack_slot<ZT>(vals[(uint32_t)e]);
+            for (int t = i + 1; t < F; ++t) {
+                const unsigned long long x = keys[t];
+                if ((uint32_t)(x >> 32) != col) break;
+                acc = MulApply<ZT, ZT>::f(add, acc, unpack_slot<ZT>(vals[(uint32_t)x]));
+            }
+            p.c_col[base + rank] = col; cval[base + rank] = acc;
+        }
+        cnt += total;
+    }
+}
+
 template <typename XT, typename ZT, int ADD, int MUL, bool NUMERIC>
 __global__ void __launch_bounds__(512) spa_kernel(const GemmArgs p) {
     typedef typename SlotWord<ZT>::W W;
@@ -902,12 +1031,15 @@ static GrB_Info spgemm_unmasked(const Csr &A, const Csr &B, const void *aval, co
     GB_TRY(dalloc(&T.col, (size_t)nnz, err));
     GB_TRY(dmalloc(&T.val, (size_t)nnz * tc_size(zt) + 16, err));
     g.c_ptr = T.rowptr; g.c_col = T.col; g.c_val = T.val;
-    // ---- numeric
+    // ---- numeric (shared-memory bins: expand-sort-compress unless B200GRB_SPGEMM_ESC=0 selects the hash kernels)
+    const bool esc = tunables().spgemm_esc;
     if (bins.count[1]) {
         g.rows = bins.rows + bins.offset[1]; g.nbin = bins.count[1]; g.table = SMALL_TABLE;
         const size_t sm = numeric_smem(SMALL_TABLE, 8, wsize);
 #define K_SMALL(XT, ZT, A_, M_) hash_numeric_kernel<XT, ZT, A_, M_, true><<<(unsigned)ceil_div(g.nbin, 8), 256, sm, G.stream>>>(g)
-        GB_FOR_SEMIRING(xt, zt, add, mul, K_SMALL, err); GB_LAUNCHED();
+#define K_ESC_SMALL(XT, ZT, A_, M_) esc_numeric_kernel<XT, ZT, A_, M_, true><<<(unsigned)ceil_div(g.nbin, 8), 256, ESC_SMEM_SMALL, G.stream>>>(g)
+        if (esc) GB_FOR_SEMIRING(xt, zt, add, mul, K_ESC_SMALL, err); else GB_FOR_SEMIRING(xt, zt, add, mul, K_SMALL, err);
+        GB_LAUNCHED();
     }
     if (bins.count[2]) {
         g.rows = bins.rows + bins.offset[2]; g.nbin = bins.count[2]; g.table = MEDIUM_TABLE;
@@ -915,7 +1047,9 @@ static GrB_Info spgemm_unmasked(const Csr &A, const Csr &B, const void *aval, co
 #define K_MEDIUM(XT, ZT, A_, M_) do { \
         cudaFuncSetAttribute(hash_numeric_kernel<XT, ZT, A_, M_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
         hash_numeric_kernel<XT, ZT, A_, M_, false><<<(unsigned)g.nbin, 256, sm, G.stream>>>(g); } while (0)
-        GB_FOR_SEMIRING(xt, zt, add, mul, K_MEDIUM, err); GB_LAUNCHED();
+#define K_ESC_MEDIUM(XT, ZT, A_, M_) esc_numeric_kernel<XT, ZT, A_, M_, false><<<(unsigned)g.nbin, 256, ESC_SMEM_MEDIUM, G.stream>>>(g)
+        if (esc) GB_FOR_SEMIRING(xt, zt, add, mul, K_ESC_MEDIUM, err); else GB_FOR_SEMIRING(xt, zt, add, mul, K_MEDIUM, err);
+        GB_LAUNCHED();
     }
     if (bins.count[3]) {
         g.rows = bins.rows + bins.offset[3]; g.nbin = bins.count[3]; g.queue = queue + 1;

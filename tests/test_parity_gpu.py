@@ -407,6 +407,37 @@ def test_rmat_unmasked_spgemm_matches_scipy():
     assert np.allclose(C2.to_csr()[2], R2.data, rtol=1e-6)
 
 
+@pytest.mark.parametrize("typ,sr", [(FP32, "PLUS_TIMES"), (FP64, "PLUS_SECOND"), (INT64, "PLUS_TIMES"), (FP32, "MIN_PLUS"), (BOOL, "LOR_LAND"), (UINT8, "MAX_FIRST")])
+def test_unmasked_spgemm_esc_equals_hash_and_scipy(typ, sr, monkeypatch):
+    """The expand-sort-compress numeric kernels (small bin: a warp per row, medium bin: a CTA per row) against the hash kernels they
+    replace (B200GRB_SPGEMM_ESC=0) -- pattern and every value, bit for bit (quarter-valued inputs: every fold order gives the same
+    sum) -- and, for PLUS_TIMES, against scipy.  The graph has rows in all three bins."""
+    n, indptr, indices = _rmat(12)
+    rng = np.random.default_rng(8)
+    if typ in (FP32, FP64):
+        vals = (rng.integers(1, 9, len(indices)) / 4.0).astype(typ.dtype)
+    elif typ is BOOL:
+        vals = np.ones(len(indices), np.bool_)
+    else:
+        vals = rng.integers(1, 4, len(indices)).astype(typ.dtype)
+    A = Matrix.from_csr(indptr, indices, vals, n, n, typ)
+    semiring = getattr(typ, sr)
+    out = {}
+    for esc in ("1", "0"):
+        monkeypatch.setenv("B200GRB_SPGEMM_ESC", esc)
+        gb.lib.B200_reload_tunables()
+        out[esc] = A.mxm(A, semiring=semiring).to_csr()
+    monkeypatch.delenv("B200GRB_SPGEMM_ESC")
+    gb.lib.B200_reload_tunables()
+    for a, b in zip(out["1"], out["0"]):
+        assert np.array_equal(a, b)
+    if sr == "PLUS_TIMES":
+        S = sp.csr_matrix((vals.astype(np.float64), indices, indptr), shape=(n, n))
+        R = (S @ S).tocsr(); R.sort_indices()
+        Cp, Cj, Cx = out["1"]
+        assert np.array_equal(Cp, R.indptr) and np.array_equal(Cj, R.indices) and np.array_equal(Cx.astype(np.float64), R.data)
+
+
 def test_sssp_min_plus_matches_scipy():
     """configs[4] shape: MIN_PLUS_FP32 sweeps with accum MIN, output aliasing the input, T0."""
     from scipy.sparse.csgraph import shortest_path
