@@ -269,7 +269,8 @@ __global__ void __launch_bounds__(HOT2_WARPS * 32, 1) spmv_run_hot2_kernel(const
         uint32_t guard = c[0] & c[7];
         if (NEED_A) {                                                       // the value loads take part too (first and last word of the lane)
             uint32_t w0, w7;
-            memcpy(&w0, &L.a[0], 4); memcpy(&w7, &L.a[7], 4);
+            if constexpr (sizeof(XT) >= 4) { memcpy(&w0, &L.a[0], 4); memcpy(&w7, &L.a[7], 4); }
+            else { w0 = (uint32_t)L.a[0]; w7 = (uint32_t)L.a[7]; }             // 1-byte values (BOOL)
             guard &= (w0 | 0x80000000u) & (w7 | 0x80000000u);
         }
         const unsigned never = __ballot_sync(0xffffffffu, guard == 0xFFFFFFFFu);
